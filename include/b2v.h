@@ -1,0 +1,132 @@
+/*
+ * b2v.h -- C ABI of libb2v.so, the B200 (sm_100a) implementation of the latent-diffusion sampling hot path of
+ * Kkuntal990/video-to-video-diffusion.  This is the drop-in boundary: the reference has no FFI layer of its own
+ * (pure PyTorch), so each entry point below states the reference Python interface it stands behind
+ * (paths are relative to the reference repository root).  The thin Python mirror of the reference classes in
+ * video-to-video-diffusion_b200/ binds exactly these symbols through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer to contiguous fp32 in the reference's own layout (NCDHW)
+ *     unless stated otherwise; timesteps are int64 like the reference's `t`;
+ *   - the caller owns all I/O buffers; an object owns its repacked fp16 weights, workspaces and CUDA graphs;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), ordered by it; an object is bound to
+ *     the device current at creation and is not re-entrant;
+ *   - return value 0 = success, <0 = error; b2v_last_error() returns the message of the calling thread's last error;
+ *   - there is no CPU fallback: every entry point fails if no sm_100 device is present.
+ */
+#ifndef B2V_H
+#define B2V_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2V_ABI_VERSION 1
+
+const char* b2v_last_error(void);
+int b2v_abi_version(void);
+/* number of kernels launched by this library in the calling process so far (bench.py's gpu_launches) */
+long long b2v_launch_count(void);
+
+/* ---------------------------------------------------------------- U-Net denoiser ---------------------------
+ * models/unet3d.py:227-413  UNet3D(latent_dim, model_channels, num_res_blocks, attention_levels, channel_mult,
+ *                                   num_heads, time_embed_dim).forward(x, t, c)                                  */
+typedef struct b2v_unet b2v_unet;
+typedef struct {
+  int latent_dim;
+  int model_channels;
+  int num_res_blocks;
+  int num_levels;
+  int channel_mult[8];
+  int attention_mask; /* bit l set <=> level l has TemporalAttention (attention_levels) */
+  int num_heads;      /* accepted for parity; the reference's attention output does not depend on it */
+  int time_embed_dim;
+} b2v_unet_desc;
+
+int b2v_unet_create(b2v_unet** out, const b2v_unet_desc* desc);
+void b2v_unet_destroy(b2v_unet* u);
+/* state_dict entry by its reference key (e.g. "down_blocks.0.0.0.conv1.conv.weight"); data = HOST fp32, copied */
+int b2v_unet_load_weight(b2v_unet* u, const char* key, const float* data, const int64_t* shape, int ndim);
+/* repack all weights (fp16 K-major tiles, folded attention); fails listing the first missing key */
+int b2v_unet_finalize(b2v_unet* u);
+/* UNet3D.forward (models/unet3d.py:357): x, c: (B,L,T,h,w); t: (B,) int64 device; eps_out: (B,L,T,h,w) */
+int b2v_unet_forward(b2v_unet* u, const float* x, const int64_t* t, const float* c, float* eps_out, int B, int T,
+                     int h, int w, void* stream);
+
+/* ---------------------------------------------------------------- samplers ---------------------------------
+ * inference/sampler.py:241-336  DDIMSampler.sample : the whole loop, one CUDA-graph replay per step, no host sync.
+ *   z_init      : the reference's initial torch.randn(shape) draw (made by the Python layer so seeds agree)
+ *   timesteps   : HOST int64[n], the reversed subset from DDIMSampler._get_timesteps (:221-239)
+ *   alphas_cumprod : HOST fp32[n_train], GaussianDiffusion.alphas_cumprod (models/diffusion.py:49)
+ *   noise       : NULL for eta == 0, else DEVICE fp32 [n][numel(z)] = the per-step torch.randn_like draws
+ *   the five NaN/Inf guards of the reference are applied on device; *nan_flag (DEVICE int, may be NULL) is set
+ *   if any of them fired.                                                                                     */
+int b2v_ddim_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
+                    const int64_t* timesteps, int n, const float* alphas_cumprod, int n_train, float eta,
+                    const float* noise, int* nan_flag, void* stream);
+/* models/diffusion.py:270-367 / inference/sampler.py:35-61  DDPM ancestral sampling, step-wise so that the caller
+ * can supply the reference's per-step torch.randn_like draw:
+ *   begin(z_init, cond) ; for t = T-1..0: step(t, coef[8], noise) ; end(z_out)
+ *   coef = {sqrt_one_minus_alphas_cumprod[t], sqrt_alphas_cumprod[t], posterior_mean_coef1[t],
+ *           posterior_mean_coef2[t], (t != 0), exp(0.5*posterior_log_variance_clipped[t]), 0, 0}  (HOST fp32)   */
+int b2v_sampler_begin(b2v_unet* u, const float* z_init, const float* cond, int B, int T, int h, int w, void* stream);
+int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise, void* stream);
+int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream);
+
+/* ---------------------------------------------------------------- VAE ---------------------------------------
+ * models/vae.py:207-306  SliceInterpolationVAE(in_channels, latent_dim, base_channels, scaling_factor)        */
+typedef struct b2v_vae b2v_vae;
+typedef struct {
+  int in_channels;
+  int latent_dim;
+  int base_channels;
+  float scaling_factor;
+} b2v_vae_desc;
+
+int b2v_vae_create(b2v_vae** out, const b2v_vae_desc* desc);
+void b2v_vae_destroy(b2v_vae* v);
+int b2v_vae_load_weight(b2v_vae* v, const char* key, const float* data, const int64_t* shape, int ndim);
+int b2v_vae_finalize(b2v_vae* v);
+/* encode (models/vae.py:235-247): x (B,Cin,T,H,W) -> z (B,L,T,H/4,W/4), already multiplied by scaling_factor */
+int b2v_vae_encode(b2v_vae* v, const float* x, float* z, int B, int T, int H, int W, void* stream);
+/* decode (models/vae.py:249-260): z (B,L,T,h,w) -> x (B,Cin,T,4h,4w), tanh-bounded */
+int b2v_vae_decode(b2v_vae* v, const float* z, float* x, int B, int T, int h, int w, void* stream);
+
+/* ---------------------------------------------------------------- glue ops ----------------------------------
+ * models/model.py:284-289  F.interpolate(z, (Dout, h, w), 'trilinear', align_corners=False) with h, w unchanged */
+int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, int HW, void* stream);
+
+/* per-op timing of the last planned program of an object, written as JSON text into buf:
+ *   [{"name": "...", "ms": .., "flops": .., "bytes": ..}, ...]  (averaged over iters CUDA-event-timed runs)   */
+int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream);
+int b2v_vae_profile(b2v_vae* v, int which /*0 encode, 1 decode*/, int iters, char* buf, size_t cap, void* stream);
+
+/* ---------------------------------------------------------------- op level (parity tests, building blocks) --
+ * activations here are NDHWC fp16 ("cl16") device buffers                                                     */
+typedef struct b2v_conv b2v_conv;
+/* kind: 0 Conv3d k3 s1 p1 | 1 Conv3d k1 | 2 Conv3d k(3,4,4) s(1,2,2) p1 | 3 ConvTranspose3d k(3,4,4) s(1,2,2) p1
+ * weight/bias: HOST fp32 in the torch layout of that module; cin1 > 0 = second input (channel concat)        */
+int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* bias, int cin0, int cin1, int cout);
+void b2v_conv_destroy(b2v_conv* c);
+/* in0/in1: cl16 [N][D][H][W][cin]; out: cl16 (out_fp32 == 0) or NCDHW fp32 (out_fp32 == 1);
+ * stats: NULL or fp32 [N][groups][2] accumulated (sum, sumsq) of the output per (sample, group)               */
+int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, float* stats,
+                     int groups, int act_tanh, int N, int D, int H, int W, void* stream);
+int b2v_nc32_to_cl16(const float* in, void* out, int B, int C, int Cpad, long long S, void* stream);
+int b2v_cl16_to_nc32(const void* in, float* out, int B, int C, int Cpad, long long S, void* stream);
+/* out = silu(gn(y)) + temb (mode 0) or silu(gn(y) + res) (mode 1); stats_in as produced by b2v_conv_forward */
+int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* gamma, const float* beta,
+                 const float* temb, const void* res, int B, long long S, int C, int G, int mode, float* stats_out,
+                 int G_out, void* stream);
+int b2v_gn_stats(const void* x, int B, long long S, int C, int G, float* stats, void* stream);
+/* DDIM update of one step, coef = device fp32[8] {c1,c2,c3,c4,sigma,..} (inference/sampler.py:299-329) */
+int b2v_ddim_update(float* z, const float* eps, const float* noise, const float* coef, long long n, int* nan_flag,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2V_H */

@@ -1,0 +1,168 @@
+"""Op-level parity on the B200: every hand-written kernel against the same op in plain PyTorch fp32
+(allow_tf32=False), called through the C ABI.  Shapes cover each conv variant, partial boxes, both sources,
+several waves of the persistent scheduler, and the heads."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(x):  # what the kernel sees: fp16-rounded operands
+    return x.half().float()
+
+
+def _report(name, got, ref, tol):
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    bad = err > tol * scale
+    msg = (f"{name}: max_abs_err={err.max().item():.4e} ref_max={scale:.4e} rel={err.max().item() / scale:.3e} "
+           f"bad={bad.sum().item()}/{bad.numel()}")
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        msg += f" first_bad_idx={idx} got={[got[tuple(i)].item() for i in idx][:4]} ref={[ref[tuple(i)].item() for i in idx][:4]}"
+    return bad.sum().item() == 0, msg
+
+
+CONV_CASES = [
+    # name, kind, cin0, cin1, cout, N, D, H, W
+    ("k1_tiny", 1, 64, 0, 64, 1, 2, 8, 8),
+    ("k3_tiny", 0, 64, 0, 64, 1, 4, 8, 8),
+    ("k3_128", 0, 128, 0, 128, 2, 6, 12, 12),
+    ("k3_256out", 0, 128, 0, 256, 1, 4, 6, 6),
+    ("k3_512out", 0, 64, 0, 512, 1, 3, 6, 6),
+    ("k3_dual", 0, 128, 64, 128, 1, 4, 12, 12),
+    ("k1_dual", 1, 128, 64, 128, 2, 4, 6, 6),
+    ("down", 2, 64, 0, 64, 1, 3, 8, 8),
+    ("down_128", 2, 128, 0, 128, 2, 4, 12, 12),
+    ("upT", 3, 64, 0, 64, 1, 3, 6, 6),
+    ("upT_128_64", 3, 128, 0, 64, 2, 4, 6, 6),
+    ("k3_waves", 0, 128, 0, 128, 2, 8, 48, 48),
+    ("k3_odd", 0, 64, 0, 64, 1, 5, 7, 9),
+]
+
+
+def _torch_conv(kind, x, w, b):
+    if kind == 0:
+        return F.conv3d(x, w, b, padding=1)
+    if kind == 1:
+        return F.conv3d(x, w, b)
+    if kind == 2:
+        return F.conv3d(x, w, b, stride=(1, 2, 2), padding=1)
+    return F.conv_transpose3d(x, w, b, stride=(1, 2, 2), padding=1)
+
+
+def _weight(kind, cin, cout, g):
+    shape = {0: (cout, cin, 3, 3, 3), 1: (cout, cin, 1, 1, 1), 2: (cout, cin, 3, 4, 4), 3: (cin, cout, 3, 4, 4)}[kind]
+    fan = cin * shape[2] * shape[3] * shape[4]
+    return torch.randn(shape, generator=g) / fan ** 0.5
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_vs_torch(cuda_dev, case):
+    from v2v_b200 import ops
+    name, kind, cin0, cin1, cout, N, D, H, W = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    cin = cin0 + cin1
+    x = torch.randn((N, cin, D, H, W), generator=g).to(cuda_dev)
+    w = _weight(kind, cin, cout, g)
+    b = torch.randn(cout, generator=g) * 0.1
+    conv = ops.Conv(kind, w, b, cin0, cin1, cout)
+    x0 = ops.to_cl16(x[:, :cin0].contiguous())
+    x1 = ops.to_cl16(x[:, cin0:].contiguous()) if cin1 else None
+    groups = 8
+    out, stats = conv(x0, x1, groups=groups)
+    torch.cuda.synchronize()
+    got = ops.from_cl16(out)
+    ref = _torch_conv(kind, _h(x), _h(w).to(cuda_dev), b.to(cuda_dev))
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    ok, msg = _report(name, got, ref, 3e-3)
+    assert ok, msg
+    # epilogue statistics = (sum, sumsq) per (sample, group) of the fp32 result
+    rg = ref.reshape(N, groups, -1)
+    ref_stats = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1)
+    ok, msg = _report(name + ".stats", stats, ref_stats, 2e-3)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("cout,tanh", [(8, False), (1, True), (4, False)])
+def test_conv_head_fp32(cuda_dev, cout, tanh):
+    from v2v_b200 import ops
+    g = torch.Generator().manual_seed(7 + cout)
+    N, cin, D, H, W = 2, 128, 4, 12, 12
+    x = torch.randn((N, cin, D, H, W), generator=g).to(cuda_dev)
+    w = _weight(0, cin, cout, g)
+    b = torch.randn(cout, generator=g) * 0.1
+    conv = ops.Conv(0, w, b, cin, 0, cout)
+    out, _ = conv(ops.to_cl16(x), out_fp32=True, tanh=tanh)
+    ref = F.conv3d(_h(x), _h(w).to(cuda_dev), b.to(cuda_dev), padding=1)
+    if tanh:
+        ref = torch.tanh(ref)
+    ok, msg = _report(f"head{cout}", out, ref, 2e-3)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("C,G,mode", [(64, 8, 0), (128, 8, 0), (128, 32, 1), (64, 32, 1), (256, 32, 1), (512, 8, 0)])
+def test_gn_apply_vs_torch(cuda_dev, C, G, mode):
+    from v2v_b200 import ops
+    g = torch.Generator().manual_seed(C + G + mode)
+    B, D, H, W = 2, 3, 6, 10
+    y = (torch.randn((B, C, D, H, W), generator=g) * 1.7 + 0.3).to(cuda_dev)
+    gamma = (torch.randn(C, generator=g) * 0.5 + 1).to(cuda_dev)
+    beta = (torch.randn(C, generator=g) * 0.2).to(cuda_dev)
+    temb = torch.randn((B, C), generator=g).to(cuda_dev)
+    res = torch.randn((B, C, D, H, W), generator=g).to(cuda_dev)
+    y16 = ops.to_cl16(y)
+    stats = ops.gn_stats(y16, G)
+    Gout = 32 if C % 32 == 0 else 8
+    if mode == 0:
+        out, so = ops.gn_apply(y16, stats, gamma, beta, G, temb=temb, mode=0, groups_out=Gout)
+        ref = F.silu(F.group_norm(_h(y), G, gamma, beta, 1e-5)) + temb[:, :, None, None, None]
+    else:
+        out, so = ops.gn_apply(y16, stats, gamma, beta, G, res=ops.to_cl16(res), mode=1, groups_out=Gout)
+        ref = F.silu(F.group_norm(_h(y), G, gamma, beta, 1e-5) + _h(res))
+    got = ops.from_cl16(out)
+    ok, msg = _report(f"gn{C}/{G}/{mode}", got, ref, 2e-3)
+    assert ok, msg
+    rg = got.reshape(B, Gout, -1)
+    ref_so = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1)
+    ok, msg = _report("gn.stats_out", so, ref_so, 1e-3)
+    assert ok, msg
+
+
+def test_ddim_update_bit_exact(cuda_dev):
+    """the scheduler update reproduces the reference's eager fp32 chain bit for bit (inference/sampler.py:299-329)"""
+    from v2v_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn((2, 8, 6, 12, 12), generator=g).to(cuda_dev)
+    eps = torch.randn((2, 8, 6, 12, 12), generator=g).to(cuda_dev)
+    for a_t, a_prev in [(2.4283e-10, 8.7619e-4), (0.492096, 0.51), (0.9977, 1.0)]:
+        alpha_t = torch.tensor(a_t, device=cuda_dev)
+        alpha_prev = torch.tensor(a_prev, device=cuda_dev)
+        sqrt_alpha_t = torch.sqrt(alpha_t + 1e-8)
+        s1m = torch.sqrt(1 - alpha_t + 1e-8)
+        z0 = (z - s1m * eps) / (sqrt_alpha_t + 1e-8)
+        z0 = torch.clamp(z0, -10.0, 10.0)
+        ref = torch.sqrt(alpha_prev + 1e-8) * z0 + torch.sqrt(1 - alpha_prev + 1e-8) * eps
+        coef = torch.stack([s1m, sqrt_alpha_t + 1e-8, torch.sqrt(alpha_prev + 1e-8), torch.sqrt(1 - alpha_prev + 1e-8),
+                            torch.zeros((), device=cuda_dev)] + [torch.zeros((), device=cuda_dev)] * 3).float()
+        zz = z.clone()
+        flag = ops.ddim_update(zz, eps, coef)
+        assert torch.equal(zz, ref), (zz - ref).abs().max().item()
+        assert flag.item() == 0
+    # NaN guard: non-finite eps is replaced like nan_to_num(nan=0, posinf=1, neginf=-1) and flagged
+    eps2 = eps.clone()
+    eps2[0, 0, 0, 0, 0] = float("nan")
+    eps2[0, 0, 0, 0, 1] = float("inf")
+    zz = z.clone()
+    flag = ops.ddim_update(zz, eps2, coef)
+    assert flag.item() == 1 and torch.isfinite(zz).all()
+
+
+def test_upsample_depth_vs_torch(cuda_dev):
+    from v2v_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn((2, 8, 8, 12, 12), generator=g).to(cuda_dev)
+    got = ops.upsample_depth(z, 48)
+    ref = F.interpolate(z, size=(48, 12, 12), mode="trilinear", align_corners=False)
+    assert (got - ref).abs().max().item() <= 1e-6

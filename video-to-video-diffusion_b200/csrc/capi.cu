@@ -1,0 +1,196 @@
+// extern "C" surface of libb2v.so (declared in include/b2v.h)
+#include <string.h>
+
+#include "unet.h"
+#include "vae.h"
+
+using namespace b2v;
+
+struct b2v_unet {
+  UNet u;
+};
+struct b2v_vae {
+  VAE v;
+};
+struct b2v_conv {
+  ConvLayer L;
+};
+
+static int check_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device (libb2v has no CPU fallback)");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail("libb2v is built for sm_100a (B200) only; found compute capability major " + std::to_string(major));
+  return 0;
+}
+
+static int store_weight(WeightMap& wm, bool finalized, const char* key, const float* data, const int64_t* shape,
+                        int ndim) {
+  if (finalized) return fail("weights already finalized");
+  if (!key || !data || ndim < 0 || ndim > 8) return fail("load_weight: bad arguments");
+  HostTensor t;
+  long long n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  t.data.assign(data, data + n);
+  wm[key] = std::move(t);
+  return 0;
+}
+
+static int write_json(const std::string& js, char* buf, size_t cap) {
+  if (js.size() + 1 > cap) return fail("profile: buffer too small (" + std::to_string(js.size() + 1) + " needed)");
+  memcpy(buf, js.c_str(), js.size() + 1);
+  return 0;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* b2v_last_error(void) { return g_err.c_str(); }
+int b2v_abi_version(void) { return B2V_ABI_VERSION; }
+long long b2v_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------ U-Net
+int b2v_unet_create(b2v_unet** out, const b2v_unet_desc* d) {
+  if (!out || !d) return fail("unet_create: null argument");
+  if (check_device()) return -1;
+  if (d->num_levels < 1 || d->num_levels > 8 || d->num_res_blocks < 1) return fail("unet_create: bad descriptor");
+  b2v_unet* u = new b2v_unet();
+  u->u.desc = *d;
+  *out = u;
+  return 0;
+}
+void b2v_unet_destroy(b2v_unet* u) { delete u; }
+int b2v_unet_load_weight(b2v_unet* u, const char* key, const float* data, const int64_t* shape, int ndim) {
+  return store_weight(u->u.wm, u->u.finalized, key, data, shape, ndim);
+}
+int b2v_unet_finalize(b2v_unet* u) { return u->u.finalize(); }
+int b2v_unet_forward(b2v_unet* u, const float* x, const int64_t* t, const float* c, float* eps_out, int B, int T,
+                     int h, int w, void* stream) {
+  return u->u.forward(x, (const long long*)t, c, eps_out, B, T, h, w, (cudaStream_t)stream);
+}
+int b2v_ddim_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
+                    const int64_t* timesteps, int n, const float* alphas_cumprod, int n_train, float eta,
+                    const float* noise, int* nan_flag, void* stream) {
+  return u->u.ddim_sample(z_init, cond, z_out, B, T, h, w, (const long long*)timesteps, n, alphas_cumprod, n_train,
+                          eta, noise, nan_flag, (cudaStream_t)stream);
+}
+int b2v_sampler_begin(b2v_unet* u, const float* z_init, const float* cond, int B, int T, int h, int w, void* stream) {
+  return u->u.sampler_begin(z_init, cond, B, T, h, w, (cudaStream_t)stream);
+}
+int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise, void* stream) {
+  return u->u.ddpm_step((long long)t, coef, noise, (cudaStream_t)stream);
+}
+int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) { return u->u.sampler_end(z_out, (cudaStream_t)stream); }
+int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream) {
+  if (!u->u.last) return fail("unet_profile: run a forward first");
+  std::string js;
+  if (u->u.last->fwd.profile(iters, (cudaStream_t)stream, js)) return -1;
+  return write_json(js, buf, cap);
+}
+
+// ------------------------------------------------------------------ VAE
+int b2v_vae_create(b2v_vae** out, const b2v_vae_desc* d) {
+  if (!out || !d) return fail("vae_create: null argument");
+  if (check_device()) return -1;
+  b2v_vae* v = new b2v_vae();
+  v->v.desc = *d;
+  *out = v;
+  return 0;
+}
+void b2v_vae_destroy(b2v_vae* v) { delete v; }
+int b2v_vae_load_weight(b2v_vae* v, const char* key, const float* data, const int64_t* shape, int ndim) {
+  return store_weight(v->v.wm, v->v.finalized, key, data, shape, ndim);
+}
+int b2v_vae_finalize(b2v_vae* v) { return v->v.finalize(); }
+int b2v_vae_encode(b2v_vae* v, const float* x, float* z, int B, int T, int H, int W, void* stream) {
+  return v->v.encode(x, z, B, T, H, W, (cudaStream_t)stream);
+}
+int b2v_vae_decode(b2v_vae* v, const float* z, float* x, int B, int T, int h, int w, void* stream) {
+  return v->v.decode(z, x, B, T, h, w, (cudaStream_t)stream);
+}
+int b2v_vae_profile(b2v_vae* v, int which, int iters, char* buf, size_t cap, void* stream) {
+  if (which < 0 || which > 1 || !v->v.last[which]) return fail("vae_profile: run encode/decode first");
+  std::string js;
+  if (v->v.last[which]->prog.profile(iters, (cudaStream_t)stream, js)) return -1;
+  return write_json(js, buf, cap);
+}
+
+// ------------------------------------------------------------------ glue / op level
+int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, int HW, void* stream) {
+  if (check_device()) return -1;
+  launch_upsample_depth(in, out, BC, Din, Dout, HW, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* bias, int cin0, int cin1, int cout) {
+  if (check_device()) return -1;
+  std::string err;
+  if (conv_setup_kernels(err)) return fail(err);
+  b2v_conv* c = new b2v_conv();
+  if (conv_layer_init(c->L, kind, weight, bias, cin0, cin1, cout, err)) {
+    delete c;
+    return fail(err);
+  }
+  *out = c;
+  return 0;
+}
+void b2v_conv_destroy(b2v_conv* c) {
+  if (c) conv_layer_free(c->L);
+  delete c;
+}
+int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, float* stats, int groups,
+                     int act_tanh, int N, int D, int H, int W, void* stream) {
+  ConvPlan P;
+  std::string err;
+  if (conv_plan(P, c->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, out_fp32 ? OUT_F32 : OUT_CL16, stats,
+                groups, act_tanh ? ACT_TANH : ACT_NONE, err))
+    return fail(err);
+  conv_launch(P, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_nc32_to_cl16(const float* in, void* out, int B, int C, int Cpad, long long S, void* stream) {
+  launch_nc32_to_cl16(in, (__half*)out, B, C, Cpad, S, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_cl16_to_nc32(const void* in, float* out, int B, int C, int Cpad, long long S, void* stream) {
+  launch_cl16_to_nc32((const __half*)in, out, B, C, Cpad, S, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* gamma, const float* beta,
+                 const float* temb, const void* res, int B, long long S, int C, int G, int mode, float* stats_out,
+                 int G_out, void* stream) {
+  if (C % 8 || C / 8 > 256) return fail("gn_apply: C must be a multiple of 8 and <= 2048");
+  launch_gn_apply((const __half*)y, (__half*)out, stats_in, gamma, beta, temb, C, (const __half*)res, B, S, C, G, 1e-5f,
+                  mode, stats_out, G_out, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_gn_stats(const void* x, int B, long long S, int C, int G, float* stats, void* stream) {
+  launch_gn_stats((const __half*)x, B, S, C, G, stats, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_ddim_update(float* z, const float* eps, const float* noise, const float* coef, long long n, int* nan_flag,
+                    void* stream) {
+  launch_ddim_update(z, eps, noise, coef, nullptr, 0, n, nan_flag, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,340 @@
+#include "conv_host.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+namespace b2v {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, std::string& err) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    err = "cuTensorMapEncodeTiled entry point not available";
+    return -1;
+  }
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu box %u %u %u", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0],
+             box[1], box[2]);
+    err = buf;
+    return -1;
+  }
+  return 0;
+}
+
+static int g_sms = 0;
+int device_sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+int conv_setup_kernels(std::string& err) {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(conv_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<16>::SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<256>::SMEM);
+  if (e != cudaSuccess) {
+    err = std::string("cudaFuncSetAttribute(conv_igemm): ") + cudaGetErrorString(e);
+    return -1;
+  }
+  return 0;
+}
+
+static inline int32_t enc_tap(int map, int dd, int dh, int dw) {
+  return (map << 24) | ((dd + 8) << 16) | ((dh + 8) << 8) | (dw + 8);
+}
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
+
+int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int cin0, int cin1, int cout,
+                    std::string& err) {
+  L = ConvLayer();
+  L.kind = kind;
+  L.cin0 = cin0;
+  L.cin1 = cin1;
+  L.cout = cout;
+  if (cout <= 16) L.bn = 16;
+  else if (cout % 256 == 0) L.bn = 256;
+  else if (cout % 128 == 0) L.bn = 128;
+  else if (cout % 64 == 0) L.bn = 64;
+  else {
+    err = "conv: Cout must be <= 16 or a multiple of 64";
+    return -1;
+  }
+  L.cout_pad = (cout + L.bn - 1) / L.bn * L.bn;
+  const bool packed = (kind == CONV_K3_PACKW || kind == CONV_K3_PACKALL);
+  if (packed) {
+    if (cin1) {
+      err = "conv: packed kinds are single-source";
+      return -1;
+    }
+    L.cin0_pad = pad64(cin0 * (kind == CONV_K3_PACKW ? 3 : 27));
+  } else {
+    if (cin0 % 64 || cin1 % 64) {
+      err = "conv: Cin must be a multiple of 64 (use a packed kind for small Cin)";
+      return -1;
+    }
+    L.cin0_pad = cin0;
+    L.cin1_pad = cin1;
+  }
+  const int cin = cin0 + cin1;
+  const int K = L.cin0_pad + L.cin1_pad;
+  int kd_n = 3, kh_n = 3, kw_n = 3;
+  switch (kind) {
+    case CONV_K3: L.ntaps = 27; break;
+    case CONV_K1: L.ntaps = 1; kd_n = kh_n = kw_n = 1; break;
+    case CONV_DOWN: L.ntaps = 48; kh_n = kw_n = 4; break;
+    case CONV_UPT: L.ntaps = 12; L.nclass = 4; kh_n = kw_n = 4; break;
+    case CONV_K3_PACKW: L.ntaps = 9; break;
+    case CONV_K3_PACKALL: L.ntaps = 1; break;
+    default: err = "conv: unknown kind"; return -1;
+  }
+  const int nt = L.ntaps * L.nclass;
+  std::vector<__half> wp((size_t)nt * L.cout_pad * K, __float2half(0.f));
+  auto W = [&](int t, int co, int k) -> __half& { return wp[((size_t)t * L.cout_pad + co) * K + k]; };
+  // torch Conv3d weight index [co][ci][kd][kh][kw]
+  auto wc = [&](int co, int ci, int kd, int kh, int kw) {
+    return w[((((size_t)co * cin + ci) * kd_n + kd) * kh_n + kh) * kw_n + kw];
+  };
+  if (kind == CONV_K3 || kind == CONV_K1) {
+    for (int kd = 0; kd < kd_n; ++kd)
+      for (int kh = 0; kh < kh_n; ++kh)
+        for (int kw = 0; kw < kw_n; ++kw) {
+          const int t = (kd * kh_n + kh) * kw_n + kw;
+          L.taps[t] = (kind == CONV_K1) ? enc_tap(0, 0, 0, 0) : enc_tap(0, kd - 1, kh - 1, kw - 1);
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+        }
+  } else if (kind == CONV_DOWN) {
+    // input index 2*o + k - 1  ->  parity view p, offset dlt:  k=0:(1,-1) 1:(0,0) 2:(1,0) 3:(0,+1)
+    static const int par[4] = {1, 0, 1, 0}, dlt[4] = {-1, 0, 0, 1};
+    for (int kd = 0; kd < 3; ++kd)
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          const int t = (kd * 4 + kh) * 4 + kw;
+          L.taps[t] = enc_tap(par[kh] * 2 + par[kw], kd - 1, dlt[kh], dlt[kw]);
+          for (int co = 0; co < cout; ++co)
+            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+        }
+  } else if (kind == CONV_UPT) {
+    // out(od, 2j+ph, 2i+pw) = sum in(od+1-kd, j+dh, i+dw) * w[ci][co][kd][kh][kw]
+    //   ph=0: kh in {1 (dh 0), 3 (dh -1)};  ph=1: kh in {0 (dh +1), 2 (dh 0)}
+    static const int ks[2][2] = {{1, 3}, {0, 2}}, ds[2][2] = {{0, -1}, {1, 0}};
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        for (int kd = 0; kd < 3; ++kd)
+          for (int a = 0; a < 2; ++a)
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int cls = ph * 2 + pw;
+              const int t = cls * 12 + (kd * 2 + a) * 2 + c2;
+              const int kh = ks[ph][a], kw = ks[pw][c2];
+              L.taps[t] = enc_tap(0, 1 - kd, ds[ph][a], ds[pw][c2]);
+              for (int co = 0; co < cout; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                  W(t, co, ci) = __float2half_rn(w[((((size_t)ci * cout + co) * 3 + kd) * 4 + kh) * 4 + kw]);
+            }
+  } else if (kind == CONV_K3_PACKW) {
+    for (int kd = 0; kd < 3; ++kd)
+      for (int kh = 0; kh < 3; ++kh) {
+        const int t = kd * 3 + kh;
+        L.taps[t] = enc_tap(0, kd - 1, kh - 1, 0);
+        for (int co = 0; co < cout; ++co)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int ci = 0; ci < cin; ++ci) W(t, co, kw * cin + ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+      }
+  } else {  // PACKALL
+    L.taps[0] = enc_tap(0, 0, 0, 0);
+    for (int co = 0; co < cout; ++co)
+      for (int tp = 0; tp < 27; ++tp)
+        for (int ci = 0; ci < cin; ++ci)
+          W(0, co, tp * cin + ci) = __float2half_rn(wc(co, ci, tp / 9, (tp / 3) % 3, tp % 3));
+  }
+  std::vector<float> bp(L.cout_pad, 0.f);
+  if (b)
+    for (int i = 0; i < cout; ++i) bp[i] = b[i];
+  cudaError_t e = cudaMalloc(&L.w, wp.size() * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&L.bias, bp.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(L.w, wp.data(), wp.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(L.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    err = std::string("conv weights upload: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)L.cout_pad, (cuuint64_t)nt};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * L.cout_pad * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)L.bn, 1};
+  return encode_map(&L.tmB, L.w, 3, dims, strides, box, err);
+}
+
+void conv_layer_free(ConvLayer& L) {
+  if (L.w) cudaFree(L.w);
+  if (L.bias) cudaFree(L.bias);
+  L.w = nullptr;
+  L.bias = nullptr;
+}
+
+// choose the (bw,bh,bd) box of <=128 positions that covers the WxHxD grid with the fewest tiles
+static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
+  long long best = -1;
+  for (int w = 1; w <= 128 && w <= W; ++w)
+    for (int h = 1; h * w <= 128 && h <= H; ++h) {
+      int d = 128 / (w * h);
+      if (d > D) d = D;
+      if (d < 1) continue;
+      const long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
+      const long long score = tiles * 4096 - w * 8 - h;  // fewer tiles, then longer contiguous runs
+      if (best < 0 || score < best) {
+        best = score;
+        bw = w;
+        bh = h;
+        bd = d;
+      }
+    }
+}
+
+int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err) {
+  memset(&P, 0, sizeof(P));
+  ConvParams& p = P.p;
+  P.bn = L.bn;
+  if ((L.cin1 != 0) != (in1 != nullptr)) {
+    err = "conv_plan: second source mismatch";
+    return -1;
+  }
+  if (out_mode == OUT_CL16 && L.bn == 16) {
+    err = "conv_plan: Cout<=16 layers write fp32";
+    return -1;
+  }
+  int gW = W, gH = H, gD = D;  // grid of logical output positions
+  if (L.kind == CONV_DOWN) {
+    if ((W | H) & 1) {
+      err = "conv_plan: strided conv needs even H, W";
+      return -1;
+    }
+    gW = W / 2;
+    gH = H / 2;
+  }
+  p.W = gW;
+  p.H = gH;
+  p.D = gD;
+  choose_box(gW, gH, gD, p.bw, p.bh, p.bd);
+  p.rows_valid = p.bw * p.bh * p.bd;
+  p.tiles_w = (gW + p.bw - 1) / p.bw;
+  p.tiles_h = (gH + p.bh - 1) / p.bh;
+  p.tiles_d = (gD + p.bd - 1) / p.bd;
+  p.batch = N;
+  p.n_tiles = L.cout_pad / L.bn;
+  p.nclass = L.nclass;
+  p.ntaps = L.ntaps;
+  p.src_chunks0 = L.cin0_pad / 64;
+  p.src_chunks1 = L.cin1_pad / 64;
+  memcpy(p.taps, L.taps, sizeof(p.taps));
+  p.tmB = L.tmB;
+  p.bias = L.bias;
+  p.stats = stats;
+  p.groups = groups;
+  p.cpg = groups ? L.cout / groups : 1;
+  if (stats && (p.cpg < 2 || (p.cpg & (p.cpg - 1)))) {
+    err = "conv_plan: channels per group must be a power of two >= 2";
+    return -1;
+  }
+  p.cout_valid = L.cout;
+  p.out_mode = out_mode;
+  p.act = act;
+  p.out = out;
+
+  // A tensor maps
+  cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+  const __half* srcs[2] = {in0, in1};
+  const int cpads[2] = {L.cin0_pad, L.cin1_pad};
+  if (L.kind == CONV_DOWN) {
+    const cuuint64_t C = cpads[0];
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        cuuint64_t dims[5] = {C, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t st[4] = {2 * C * 2, 2 * (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                            (cuuint64_t)D * H * W * C * 2};
+        const __half* base = in0 + ((size_t)ph * W + pw) * C;
+        if (encode_map(&p.tmA[ph * 2 + pw], base, 5, dims, st, box, err)) return -1;
+      }
+  } else {
+    for (int s = 0; s < 2; ++s) {
+      if (!srcs[s]) continue;
+      const cuuint64_t C = cpads[s];
+      cuuint64_t dims[5] = {C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+      cuuint64_t st[4] = {C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+      if (encode_map(&p.tmA[s], srcs[s], 5, dims, st, box, err)) return -1;
+    }
+  }
+
+  // output strides (elements)
+  const long long oW = (L.kind == CONV_UPT) ? 2LL * W : gW, oH = (L.kind == CONV_UPT) ? 2LL * H : gH, oD = gD;
+  const long long up = (L.kind == CONV_UPT) ? 2 : 1;
+  if (out_mode == OUT_CL16) {
+    const long long C = L.cout;
+    p.sC = 1;
+    p.sW = up * C;
+    p.sH = up * oW * C;
+    p.sD = oH * oW * C;
+    p.sN = oD * oH * oW * C;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) p.cls_off[ph * 2 + pw] = (ph * oW + pw) * C;
+  } else {
+    p.sC = oD * oH * oW;
+    p.sW = up;
+    p.sH = up * oW;
+    p.sD = oH * oW;
+    p.sN = (long long)L.cout * oD * oH * oW;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) p.cls_off[ph * 2 + pw] = ph * oW + pw;
+  }
+  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N * p.nclass * p.n_tiles;
+  const int sms = device_sm_count();
+  P.grid = (int)(total < sms ? total : sms);
+  const double taps_real = (L.kind == CONV_K1) ? 1 : (L.kind == CONV_DOWN || L.kind == CONV_UPT) ? 48 : 27;
+  const double pos = (L.kind == CONV_UPT) ? (double)N * D * H * W : (double)N * gD * gH * gW;
+  P.flops = 2.0 * pos * taps_real * (double)(L.cin0 + L.cin1) * (double)L.cout;
+  return 0;
+}
+
+void conv_launch(const ConvPlan& P, cudaStream_t st) {
+  switch (P.bn) {
+    case 16: conv_igemm_kernel<16><<<P.grid, 192, ConvCfg<16>::SMEM, st>>>(P.p); break;
+    case 64: conv_igemm_kernel<64><<<P.grid, 192, ConvCfg<64>::SMEM, st>>>(P.p); break;
+    case 128: conv_igemm_kernel<128><<<P.grid, 192, ConvCfg<128>::SMEM, st>>>(P.p); break;
+    default: conv_igemm_kernel<256><<<P.grid, 192, ConvCfg<256>::SMEM, st>>>(P.p); break;
+  }
+}
+
+}  // namespace b2v

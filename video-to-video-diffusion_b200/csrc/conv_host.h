@@ -1,0 +1,50 @@
+// Host side of the implicit-GEMM convolution: weight repacking, TMA tensor maps, tile geometry, launch.
+#pragma once
+#include <string>
+
+#include "conv_igemm.cuh"
+
+namespace b2v {
+
+enum ConvKind {
+  CONV_K3 = 0,        // 3x3x3, stride 1, pad 1                     (torch Conv3d weight [Co][Ci][3][3][3])
+  CONV_K1 = 1,        // 1x1x1                                      ([Co][Ci][1][1][1])
+  CONV_DOWN = 2,      // (3,4,4) stride (1,2,2) pad 1               ([Co][Ci][3][4][4])
+  CONV_UPT = 3,       // ConvTranspose3d (3,4,4) stride (1,2,2) p1  ([Ci][Co][3][4][4])
+  CONV_K3_PACKW = 4,  // 3x3x3 on an input whose 3 w-taps are packed into the channel slot (slot = kw*Ci + ci)
+  CONV_K3_PACKALL = 5 // 3x3x3 on an input whose 27 taps are packed into the channel slot (slot = tap*Ci + ci)
+};
+
+struct ConvLayer {
+  int kind = 0;
+  int cin0 = 0, cin1 = 0;          // real input channels per source (cin1 = 0: single source)
+  int cin0_pad = 0, cin1_pad = 0;  // channels of the A tensors (multiples of 64)
+  int cout = 0, cout_pad = 0, bn = 0;
+  int ntaps = 0, nclass = 1;
+  __half* w = nullptr;   // device [nclass*ntaps][cout_pad][cin0_pad+cin1_pad]
+  float* bias = nullptr; // device [cout_pad]
+  CUtensorMap tmB;
+  int32_t taps[48];
+};
+
+struct ConvPlan {
+  ConvParams p;
+  int bn = 0;
+  int grid = 0;
+  double flops = 0;  // algorithmic 2*MAC of the reference convolution (no padding / packing waste)
+};
+
+// w_host / b_host: fp32 host arrays in the torch layout of `kind`; b_host may be null (zero bias)
+int conv_layer_init(ConvLayer& L, int kind, const float* w_host, const float* b_host, int cin0, int cin1, int cout,
+                    std::string& err);
+void conv_layer_free(ConvLayer& L);
+
+// in0/in1: NDHWC fp16 [N][D][H][W][cin*_pad]; (D,H,W) are the INPUT dims.
+// out_mode OUT_CL16: out is NDHWC fp16 with cout channels; OUT_F32: out is NCDHW fp32 with cout channels.
+int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err);
+void conv_launch(const ConvPlan& P, cudaStream_t st);
+int conv_setup_kernels(std::string& err);  // opt-in to large dynamic shared memory; call once per device
+int device_sm_count();
+
+}  // namespace b2v

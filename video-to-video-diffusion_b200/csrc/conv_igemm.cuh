@@ -1,0 +1,275 @@
+// Implicit-GEMM Conv3d / ConvTranspose3d for sm_100a.
+//
+// Replaces the cuDNN/oneDNN convolutions the reference reaches through nn.Conv3d / nn.ConvTranspose3d
+// (reference models/unet3d.py:56,96,102,204,218,257,331 and models/vae.py:27,45,65,86,134,137,161,188).
+//
+//   activations : NDHWC fp16 ("cl16"), channels padded to a multiple of 64
+//   weights     : [tap][Cout_pad][Cin_total] fp16 (K-major rows for the B operand)
+//   M tile      : a (bd x bh x bw) box of <=128 output positions of one sample, fetched per filter tap with
+//                 one 5-D TMA box load whose start coordinate is shifted by the tap offset; out-of-bounds
+//                 elements are zero-filled by TMA, which IS the conv zero padding
+//   K loop      : taps x 64-channel chunks (x up to two sources: the U-Net skip concat is never materialised)
+//   MMA         : tcgen05.mma kind::f16, M=128 x N=BN x K=16, fp32 accumulators double-buffered in TMEM
+//   epilogue    : +bias, optional per-(sample,group) sum / sum-of-squares for the following GroupNorm,
+//                 optional tanh, store fp16 NDHWC (vectorised) or fp32 with arbitrary strides (NCDHW heads,
+//                 sub-pixel interleave of the transposed conv)
+//
+// Strided (1,2,2) convs read four parity views of the input (four tensor maps with doubled strides);
+// transposed (1,2,2) convs run as four output-parity classes of 3x2x2 taps each.
+#pragma once
+#include "ptx.cuh"
+
+namespace b2v {
+
+enum { OUT_CL16 = 0, OUT_F32 = 1 };
+enum { ACT_NONE = 0, ACT_TANH = 1 };
+
+struct ConvParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  int32_t taps[48];       // per (class, tap): (map << 24) | ((dd+8) << 16) | ((dh+8) << 8) | (dw+8)
+  long long cls_off[4];   // output element offset of each class
+  long long sN, sD, sH, sW, sC;  // output strides (elements)
+  void* out;
+  const float* bias;      // [n_tiles*BN]
+  float* stats;           // [batch][groups][2] (sum, sumsq) or nullptr
+  int bw, bh, bd, rows_valid;
+  int tiles_w, tiles_h, tiles_d, batch;
+  int n_tiles, nclass, ntaps;
+  int src_chunks0, src_chunks1;
+  int W, H, D;            // logical grid of output positions per sample and class
+  int groups, cpg, cout_valid, out_mode, act;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int SUB>
+__device__ __forceinline__ void chunk_stats(const float* v, int ncol, bool valid, float* srow, int gbase, int lane) {
+#pragma unroll
+  for (int seg = 0; seg < 32 / SUB; ++seg) {
+    if (seg * SUB < ncol) {
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < SUB; ++j) {
+        float x = valid ? v[seg * SUB + j] : 0.f;
+        s += x;
+        ss += x * x;
+      }
+      s = warp_sum(s);
+      ss = warp_sum(ss);
+      if (lane == 0) {
+        atomicAdd(srow + (gbase + seg) * 2, s);
+        atomicAdd(srow + (gbase + seg) * 2 + 1, ss);
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int NSTAGE = Cfg::NSTAGE;
+  constexpr int CH = (BN >= 32) ? 32 : 16;  // epilogue column chunk
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tfull = empty + NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
+  const int total_tiles = m_tiles * p.nclass * p.n_tiles;
+  const int chunks = p.src_chunks0 + p.src_chunks1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m = tile % m_tiles;
+        int rest = tile / m_tiles;
+        const int cls = rest % p.nclass;
+        const int n0 = (rest / p.nclass) * BN;
+        const int w0 = (m % p.tiles_w) * p.bw;
+        m /= p.tiles_w;
+        const int h0 = (m % p.tiles_h) * p.bh;
+        m /= p.tiles_h;
+        const int d0 = (m % p.tiles_d) * p.bd;
+        const int nb = m / p.tiles_d;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int tg = cls * p.ntaps + t;
+          const int32_t tp = p.taps[tg];
+          const int map = tp >> 24;
+          const int cd = d0 + ((tp >> 16) & 0xff) - 8;
+          const int chh = h0 + ((tp >> 8) & 0xff) - 8;
+          const int cw = w0 + (tp & 0xff) - 8;
+          for (int c = 0; c < chunks; ++c) {
+            const int src = (c >= p.src_chunks0) ? 1 : 0;
+            const int cc = src ? (c - p.src_chunks0) : c;
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
+            uint8_t* sa = smem + stage * Cfg::STAGE;
+            tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
+            tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN, 0);
+      const int ksteps = p.ntaps * chunks;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int k = 0; k < ksteps; ++k) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int rw = r % p.bw;
+    const int rh = (r / p.bw) % p.bh;
+    const int rd = r / (p.bw * p.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int m = tile % m_tiles;
+      int rest = tile / m_tiles;
+      const int cls = rest % p.nclass;
+      const int n0 = (rest / p.nclass) * BN;
+      const int w = (m % p.tiles_w) * p.bw + rw;
+      m /= p.tiles_w;
+      const int h = (m % p.tiles_h) * p.bh + rh;
+      m /= p.tiles_h;
+      const int d = (m % p.tiles_d) * p.bd + rd;
+      const int nb = m / p.tiles_d;
+      const bool valid = (r < p.rows_valid) && (w < p.W) && (h < p.H) && (d < p.D);
+      const long long roff = p.cls_off[cls] + nb * p.sN + d * p.sD + h * p.sH + w * p.sW;
+      float* srow = p.stats ? (p.stats + (size_t)nb * p.groups * 2) : nullptr;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        float v[CH];
+        if constexpr (CH == 32)
+          tmem_ld_32x32(taddr + c0, v);
+        else
+          tmem_ld_32x16(taddr + c0, v);
+        tmem_ld_wait();
+        const int cg = n0 + c0;
+        if (cg >= p.cout_valid) break;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + cg + j);
+        if (srow) {
+          const int gbase = cg / p.cpg;
+          const int ncol = min(CH, p.cout_valid - cg);
+          if (p.cpg >= 32) chunk_stats<32>(v, ncol, valid, srow, gbase, lane);
+          else if (p.cpg == 16) chunk_stats<16>(v, ncol, valid, srow, gbase, lane);
+          else if (p.cpg == 8) chunk_stats<8>(v, ncol, valid, srow, gbase, lane);
+          else chunk_stats<4>(v, ncol, valid, srow, gbase, lane);
+        }
+        if (p.act == ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = tanhf(v[j]);
+        }
+        if (valid) {
+          if (p.out_mode == OUT_CL16) {
+            __half* o = reinterpret_cast<__half*>(p.out) + roff + cg;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              __half2 h0 = __floats2half2_rn(v[j + 0], v[j + 1]);
+              __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+              __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+              __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2);
+              u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + roff;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (cg + j < p.cout_valid) o[(long long)(cg + j) * p.sC] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TM_COLS);
+}
+
+}  // namespace b2v

@@ -1,0 +1,114 @@
+// Host runtime shared by the U-Net and VAE objects: weight store, device buffer pool, op lists that are
+// captured into CUDA graphs, per-op CUDA-event profiling.
+#pragma once
+#include <atomic>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "conv_host.h"
+#include "ew_kernels.h"
+
+namespace b2v {
+
+extern thread_local std::string g_err;
+extern std::atomic<long long> g_launches;
+int fail(const std::string& msg);  // sets g_err, returns -1
+#define B2V_CUDA(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e__ = (x);                                                                \
+    if (e__ != cudaSuccess) return fail(std::string(#x ": ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  long long numel() const {
+    long long n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+using WeightMap = std::map<std::string, HostTensor>;
+// returns nullptr and sets g_err if missing or (when numel > 0) of the wrong size
+const HostTensor* need(const WeightMap& wm, const std::string& key, long long numel);
+
+// device arrays owned by an object
+struct DeviceStore {
+  std::vector<void*> ptrs;
+  float* upload(const float* h, size_t n);
+  float* upload(const std::vector<float>& h) { return upload(h.data(), h.size()); }
+  void* alloc(size_t bytes);
+  ~DeviceStore();
+};
+
+// caching device allocator for the activations of one program (all requests happen at build time)
+struct Pool {
+  struct Blk {
+    void* p;
+    size_t sz;
+    bool used;
+  };
+  std::vector<Blk> blks;
+  void* get(size_t bytes);
+  void put(void* p);
+  size_t total() const;
+  ~Pool();
+};
+
+struct Op {
+  std::string name;
+  double flops = 0, bytes = 0;
+  int launches = 1;
+  std::function<void(cudaStream_t)> run;
+};
+
+// a fixed op list, replayed as one CUDA graph
+struct Program {
+  std::vector<Op> ops;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  int run(cudaStream_t st);                                        // capture on first use, then graph launch
+  int run_eager(cudaStream_t st);                                  // plain launches (debug)
+  int profile(int iters, cudaStream_t st, std::string& json) const; // per-op event timing
+  ~Program();
+};
+
+struct GNW {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+  int C = 0, G = 0;
+};
+int load_gn(GNW& g, const WeightMap& wm, const std::string& prefix, int C, int G, DeviceStore& ds);
+int load_conv(ConvLayer& L, int kind, const WeightMap& wm, const std::string& prefix, int cin0, int cin1, int cout);
+int groups32(int C);  // reference _get_num_groups: largest of 32,16,8,4,2,1 dividing C
+
+// activation handle (batch is a property of the program)
+struct Act {
+  __half* p = nullptr;
+  int C = 0, D = 0, H = 0, W = 0;
+  long long S() const { return (long long)D * H * W; }
+};
+
+// op-list builder shared by the U-Net and VAE programs
+struct Builder {
+  std::vector<Op>& ops;
+  Pool& pool;
+  int B;
+  float* stats_base;
+  size_t stats_cap, stats_used = 0;
+  bool ok = true;
+  Builder(std::vector<Op>& o, Pool& p, int b, float* sb, size_t sc) : ops(o), pool(p), B(b), stats_base(sb), stats_cap(sc) {}
+  Act alloc(int C, int D, int H, int W);
+  void free(Act& a);
+  float* new_stats(int G);
+  // out_fp32 != nullptr: NCDHW fp32 head; otherwise returns a fresh cl16 activation
+  Act conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, float* stats, int groups,
+           float* out_fp32 = nullptr, int act = ACT_NONE, const float* bias_override = nullptr);
+  void gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, const float* temb,
+                int temb_stride, const Act* res, int mode, float* stats_out, int G_out);
+};
+
+}  // namespace b2v

@@ -1,0 +1,565 @@
+// HBM-bound kernels of the sampling path: GroupNorm-apply fusions, the (degenerate) temporal-attention
+// reduction, time embedding, scheduler updates, layout packs and the depth upsample.
+// Activations are NDHWC fp16 ("cl16"); latents / images at the API boundary are NCDHW fp32 ("nc32").
+// Every kernel is vectorised to 16-byte accesses along the channel (or w) axis and sized to fill 148 SMs.
+#include "ew_kernels.h"
+
+#include <math.h>
+
+namespace b2v {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+struct H8 {
+  uint4 u;
+};
+__device__ __forceinline__ void h8_to_f(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f_to_h8(const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply (+affine) fused with SiLU / time-embedding add / residual add, optional statistics
+// of the result for a following GroupNorm.  Reference: Conv3DBlock.forward + ResBlock3D.forward
+// (models/unet3d.py:70-74,116-133; models/vae.py:31-35,50-56,72-76,93-97), conv_out[0:2] (unet3d.py:328-330).
+//   mode 0: out = silu(gn(y)) + temb[b][c]           (temb may be null)
+//   mode 1: out = silu(gn(y) + res)                  (res may be null)
+// stats_in : [B][G][2] raw (sum, sumsq) over S*cpg elements, produced by the conv epilogue.
+// Grid: (blocks, B); block = C8*R threads, each thread owns 8 fixed channels and strides over rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void gn_apply_kernel(const __half* __restrict__ y_, __half* out_, const float* __restrict__ stats_in,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ temb, int temb_stride, const __half* res_, long long S,
+                                int C, int G, float eps, int mode, float* stats_out, int G_out) {
+  extern __shared__ float sm[];  // [2*C] when stats_out
+  const int C8 = C >> 3;
+  const int R = blockDim.x / C8;
+  const int cv = threadIdx.x % C8;
+  const int rr = threadIdx.x / C8;
+  const int b = blockIdx.y;
+  const int c0 = cv * 8;
+  const int cpg = C / G;
+  const float inv_n = 1.0f / ((float)S * (float)cpg);
+
+  float sc[8], sh[8], ta[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    const float s = stats_in[((size_t)b * G + g) * 2];
+    const float ss = stats_in[((size_t)b * G + g) * 2 + 1];
+    const float mean = s * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float ga = gamma[c];
+    sc[j] = ga * rstd;
+    sh[j] = beta[c] - mean * ga * rstd;
+    ta[j] = (mode == 0 && temb) ? temb[(size_t)b * temb_stride + c] : 0.f;
+  }
+  float as[8], ass[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) as[j] = ass[j] = 0.f;
+
+  const size_t base = (size_t)b * S * C;
+  const uint4* y = reinterpret_cast<const uint4*>(y_ + base);
+  uint4* out = reinterpret_cast<uint4*>(out_ + base);
+  const uint4* res = res_ ? reinterpret_cast<const uint4*>(res_ + base) : nullptr;
+
+  for (long long row = (long long)blockIdx.x * R + rr; row < S; row += (long long)gridDim.x * R) {
+    const size_t idx = (size_t)row * C8 + cv;
+    float f[8];
+    h8_to_f(y[idx], f);
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j]) + ta[j];
+    } else {
+      float rf[8];
+      if (res) {
+        h8_to_f(res[idx], rf);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rf[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j] + rf[j]);
+    }
+    const uint4 o = f_to_h8(f);
+    out[idx] = o;
+    if (stats_out) {
+      float g[8];
+      h8_to_f(o, g);  // statistics of the values the consumer will actually read
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        as[j] += g[j];
+        ass[j] += g[j] * g[j];
+      }
+    }
+  }
+  if (stats_out) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[c0 + j], as[j]);
+      atomicAdd(&sm[C + c0 + j], ass[j]);
+    }
+    __syncthreads();
+    const int cpo = C / G_out;
+    for (int g = threadIdx.x; g < G_out; g += blockDim.x) {
+      float s = 0.f, ss = 0.f;
+      for (int j = 0; j < cpo; ++j) {
+        s += sm[g * cpo + j];
+        ss += sm[C + g * cpo + j];
+      }
+      atomicAdd(&stats_out[((size_t)b * G_out + g) * 2], s);
+      atomicAdd(&stats_out[((size_t)b * G_out + g) * 2 + 1], ss);
+    }
+  }
+}
+
+void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const float* gamma, const float* beta,
+                     const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
+                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st) {
+  const int C8 = C / 8;
+  const int R = C8 >= 256 ? 1 : 256 / C8;
+  const int threads = C8 * R;
+  long long want = (S + R - 1) / R;
+  long long cap = (148LL * 8 + B - 1) / B;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  const size_t smem = stats_out ? 2 * C * sizeof(float) : 0;
+  gn_apply_kernel<<<dim3(blocks, B), threads, smem, st>>>(y, out, stats_in, gamma, beta, temb, temb_stride, res, S, C,
+                                                         G, eps, mode, stats_out, G_out);
+}
+
+// Stand-alone statistics pass (used when the producer is not one of our conv / apply kernels, and by tests).
+__global__ void gn_stats_kernel(const __half* __restrict__ x_, long long S, int C, int G, float* stats) {
+  extern __shared__ float sm[];
+  const int C8 = C >> 3, R = blockDim.x / C8, cv = threadIdx.x % C8, rr = threadIdx.x / C8, b = blockIdx.y;
+  const uint4* x = reinterpret_cast<const uint4*>(x_ + (size_t)b * S * C);
+  float as[8], ass[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) as[j] = ass[j] = 0.f;
+  for (long long row = (long long)blockIdx.x * R + rr; row < S; row += (long long)gridDim.x * R) {
+    float f[8];
+    h8_to_f(x[(size_t)row * C8 + cv], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      as[j] += f[j];
+      ass[j] += f[j] * f[j];
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[cv * 8 + j], as[j]);
+    atomicAdd(&sm[C + cv * 8 + j], ass[j]);
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      s += sm[g * cpg + j];
+      ss += sm[C + g * cpg + j];
+    }
+    atomicAdd(&stats[((size_t)b * G + g) * 2], s);
+    atomicAdd(&stats[((size_t)b * G + g) * 2 + 1], ss);
+  }
+}
+
+void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st) {
+  const int C8 = C / 8;
+  const int R = C8 >= 256 ? 1 : 256 / C8;
+  long long want = (S + R - 1) / R;
+  long long cap = (148LL * 8 + B - 1) / B;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  gn_stats_kernel<<<dim3(blocks, B), C8 * R, 2 * C * sizeof(float), st>>>(x, S, C, G, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TemporalAttention (reference models/unet3d.py:163-194).  The reference's second einsum
+// 'bhqk,bhvc->bhqc' sums k and v independently, so out[b,:,t,h,w] = (sum_k softmax) * sum_t V = sum_t V
+// for every t.  With V = Wv*GN(x)+bv this is  x + Wp*(Wv * sum_t GN(x) + T*bv) + bp.
+// attn_tsum: s[b,p,c] = sum_t GN32(x)[b,t,p,c] = gamma*rstd*(sum_t x - T*mean) + T*beta    (fp16 out)
+// (the C x C product Wp*Wv and the folded bias are built once at weight-load time; the tiny GEMM runs on
+//  the conv kernel); add_bcast_t: x[b,t,p,:] += y[b,p,:].
+// ------------------------------------------------------------------------------------------------
+__global__ void attn_tsum_kernel(const __half* __restrict__ x_, const float* __restrict__ stats,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* s_, int T,
+                                 int P, int C, int G, float eps, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C8 = C >> 3;
+  const int cv = (int)(i % C8);
+  const long long bp = i / C8;
+  const int p = (int)(bp % P);
+  const int b = (int)(bp / P);
+  const uint4* x = reinterpret_cast<const uint4*>(x_) + ((size_t)b * T * P + p) * C8 + cv;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const size_t tstride = (size_t)P * C8;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    float f[8];
+    h8_to_f(x[t * tstride], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  const int cpg = C / G;
+  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float s = stats[((size_t)b * G + g) * 2], ss = stats[((size_t)b * G + g) * 2 + 1];
+    const float mean = s * inv_n;
+    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+    o[j] = gamma[c] * rstd * (acc[j] - (float)T * mean) + (float)T * beta[c];
+  }
+  reinterpret_cast<uint4*>(s_)[i] = f_to_h8(o);
+}
+
+void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
+                      int T, int P, int C, int G, float eps, cudaStream_t st) {
+  const long long total = (long long)B * P * (C / 8);
+  attn_tsum_kernel<<<cdiv(total, 128), 128, 0, st>>>(x, stats, gamma, beta, s, T, P, C, G, eps, total);
+}
+
+__global__ void add_bcast_t_kernel(__half* x_, const __half* __restrict__ y_, int T, long long PC8, long long total) {
+  uint4* x = reinterpret_cast<uint4*>(x_);
+  const uint4* y = reinterpret_cast<const uint4*>(y_);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / (T * PC8);
+    const long long r = i % PC8;
+    float a[8], c[8];
+    h8_to_f(x[i], a);
+    h8_to_f(y[b * PC8 + r], c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += c[j];
+    x[i] = f_to_h8(a);
+  }
+}
+
+void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, cudaStream_t st) {
+  const long long PC8 = (long long)P * (C / 8);
+  const long long total = (long long)B * T * PC8;
+  int blocks = cdiv(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_bcast_t_kernel<<<blocks, 256, 0, st>>>(x, y, T, PC8, total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time embedding (reference models/unet3d.py:18-48 and the per-block time_mlp :88-91,123-125).
+//   temb_mlp : sinusoid(t) -> Linear(dim,td) -> SiLU -> Linear(td,td); stores SiLU(temb) (what every block consumes)
+//   temb_proj: all ResBlock projections at once: out[b][row] = W[row,:].silu_temb[b,:] + bias[row]
+// t comes from t_ptr[b], or from t_table[*step_ptr] when a sampler graph is replayed.
+// ------------------------------------------------------------------------------------------------
+__global__ void temb_mlp_kernel(const long long* __restrict__ t_ptr, const long long* __restrict__ t_table,
+                                const int* __restrict__ step_ptr, const float* __restrict__ freqs,
+                                const float* __restrict__ W1, const float* __restrict__ b1,
+                                const float* __restrict__ W2, const float* __restrict__ b2, float* silu_temb,
+                                int dim, int td) {
+  extern __shared__ float sm[];  // emb[dim] | h1[td]
+  float* emb = sm;
+  float* h1 = sm + dim;
+  const int b = blockIdx.x;
+  const long long t = t_table ? t_table[*step_ptr] : t_ptr[b];
+  const int half = dim / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float a = (float)t * freqs[i];
+    emb[i] = sinf(a);
+    emb[half + i] = cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < td; r += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc += W1[(size_t)r * dim + k] * emb[k];
+    acc = warp_sum(acc);
+    if (lane == 0) h1[r] = silu_f(acc + b1[r]);
+  }
+  __syncthreads();
+  for (int r = warp; r < td; r += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < td; k += 32) acc += W2[(size_t)r * td + k] * h1[k];
+    acc = warp_sum(acc);
+    if (lane == 0) silu_temb[(size_t)b * td + r] = silu_f(acc + b2[r]);
+  }
+}
+
+__global__ void temb_proj_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                 const float* __restrict__ silu_temb, float* out, int rows, int td, int B) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+    for (int k = lane; k < td; k += 32) acc += W[(size_t)warp * td + k] * silu_temb[(size_t)b * td + k];
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)b * rows + warp] = acc + bias[warp];
+  }
+}
+
+void launch_temb(const long long* t_ptr, const long long* t_table, const int* step_ptr, const float* freqs,
+                 const float* W1, const float* b1, const float* W2, const float* b2, float* silu_temb,
+                 const float* Wp, const float* bp, float* proj, int rows, int dim, int td, int B, cudaStream_t st) {
+  temb_mlp_kernel<<<B, 512, (dim + td) * sizeof(float), st>>>(t_ptr, t_table, step_ptr, freqs, W1, b1, W2, b2,
+                                                              silu_temb, dim, td);
+  temb_proj_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(Wp, bp, silu_temb, proj, rows, td, B);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scheduler updates, fp32, written with explicit round-to-nearest ops in the reference's operation order so
+// the result is bit-identical to the reference's eager elementwise chain for the same eps.
+// DDIM: reference inference/sampler.py:286-334.  coef[step] = {c1=sqrt(1-a_t+1e-8), c2=sqrt(a_t+1e-8)+1e-8,
+//        c3=sqrt(a_prev+1e-8), c4=sqrt(1-a_prev+1e-8), sigma, 0,0,0}
+// DDPM: reference models/diffusion.py:270-338.  coef[step] = {sqrt_1m_ac[t], sqrt_ac[t], coef1[t], coef2[t],
+//        (t!=0), exp(0.5*logvar[t]), 0, 0}
+// The reference's NaN guards (nan_to_num(nan=0,posinf=1,neginf=-1) when any element is non-finite) are applied
+// per element unconditionally -- identical on finite data -- and recorded in *nan_flag instead of a host sync.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nan_guard(float x, int* flag) {
+  if (isnan(x)) {
+    *flag = 1;
+    return 0.f;
+  }
+  if (isinf(x)) {
+    *flag = 1;
+    return x > 0 ? 1.f : -1.f;
+  }
+  return x;
+}
+
+__global__ void ddim_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise,
+                                   const float* __restrict__ coef_table, const int* __restrict__ step_ptr,
+                                   int step_imm, long long n, int* nan_flag) {
+  const int step = step_ptr ? *step_ptr : step_imm;
+  const float* c = coef_table + (size_t)step * 8;
+  const float c1 = c[0], c2 = c[1], c3 = c[2], c4 = c[3], sigma = c[4];
+  int flag = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float e = nan_guard(eps[i], &flag);
+    float z0 = __fdiv_rn(__fsub_rn(z[i], __fmul_rn(c1, e)), c2);
+    z0 = nan_guard(z0, &flag);
+    z0 = fminf(fmaxf(z0, -10.0f), 10.0f);
+    float zn = __fadd_rn(__fmul_rn(c3, z0), __fmul_rn(c4, e));
+    if (noise) zn = __fadd_rn(zn, __fmul_rn(sigma, noise[i]));
+    z[i] = nan_guard(zn, &flag);
+  }
+  if (flag && nan_flag) atomicOr(nan_flag, 1);
+}
+
+__global__ void ddpm_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise, Coef8 c,
+                                   long long n) {
+  const float s1m = c.v[0], sa = c.v[1], k1 = c.v[2], k2 = c.v[3], nz = c.v[4], sd = c.v[5];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float zt = z[i];
+    float z0 = __fdiv_rn(__fsub_rn(zt, __fmul_rn(s1m, eps[i])), sa);
+    z0 = fminf(fmaxf(z0, -1.0f), 1.0f);
+    const float mean = __fadd_rn(__fmul_rn(k1, z0), __fmul_rn(k2, zt));
+    z[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sd), noise[i]));
+  }
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+
+void launch_ddim_update(float* z, const float* eps, const float* noise, const float* coef_table, const int* step_ptr,
+                        int step_imm, long long n, int* nan_flag, cudaStream_t st) {
+  int blocks = cdiv(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddim_update_kernel<<<blocks, 256, 0, st>>>(z, eps, noise, coef_table, step_ptr, step_imm, n, nan_flag);
+}
+void launch_ddpm_update(float* z, const float* eps, const float* noise, const Coef8& coef, long long n,
+                        cudaStream_t st) {
+  int blocks = cdiv(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddpm_update_kernel<<<blocks, 256, 0, st>>>(z, eps, noise, coef, n);
+}
+void launch_advance_step(int* step, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(step); }
+
+// t_dev[b] = t_table[*step] (sampler graphs) or an immediate value (step-wise DDPM)
+__global__ void set_t_kernel(long long* t_dev, const long long* __restrict__ t_table, const int* __restrict__ step,
+                             long long imm, int B) {
+  const int b = threadIdx.x;
+  if (b < B) t_dev[b] = t_table ? t_table[*step] : imm;
+}
+void launch_set_t(long long* t_dev, const long long* t_table, const int* step, long long imm, int B, cudaStream_t st) {
+  const int threads = B < 64 ? 64 : B;
+  set_t_kernel<<<1, threads, 0, st>>>(t_dev, t_table, step, imm, B);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input packs.  Tiny-channel inputs (latents: 2L or 8 channels, CT slices: 1 channel) are expanded so that
+// the filter taps along w (or all 27 taps) sit in the 64-wide channel slot of one cl16 row; the remaining
+// taps are then ordinary shifted TMA boxes of the conv kernel.
+// ------------------------------------------------------------------------------------------------
+// U-Net conv_in input: cat([z, c], 1) (reference models/unet3d.py:372), slot = kw*(2L) + ch
+__global__ void pack_unet_in_kernel(const float* __restrict__ z, const float* __restrict__ c, __half* out, int L,
+                                    int D, int H, int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, d, h, w, seg)
+  if (i >= total) return;
+  const int seg = (int)(i & 7);
+  long long pos = i >> 3;
+  const int w = (int)(pos % W);
+  const long long S = (long long)D * H * W;
+  const long long b = pos / S;
+  const long long sp = pos % S;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int slot = seg * 8 + j;
+    const int kw = slot / (2 * L), ch = slot % (2 * L);
+    const int ww = w + kw - 1;
+    float v = 0.f;
+    if (kw < 3 && ww >= 0 && ww < W) {
+      const float* src = (ch < L) ? z : c;
+      const int cc = (ch < L) ? ch : ch - L;
+      v = src[((size_t)b * L + cc) * S + sp + (kw - 1)];
+    }
+    f[j] = v;
+  }
+  reinterpret_cast<uint4*>(out)[i] = f_to_h8(f);
+}
+void launch_pack_unet_in(const float* z, const float* c, __half* out, int B, int L, int D, int H, int W,
+                         cudaStream_t st) {
+  const long long total = (long long)B * D * H * W * 8;
+  pack_unet_in_kernel<<<cdiv(total, 256), 256, 0, st>>>(z, c, out, L, D, H, W, total);
+}
+
+// VAE decoder input: u = post_quant_conv(z / scaling_factor) (reference models/vae.py:259,192), 8 channels,
+// slot = kw*8 + co
+__global__ void pack_vae_dec_in_kernel(const float* __restrict__ z, const float* __restrict__ Wpq,
+                                       const float* __restrict__ bpq, float scaling, __half* out, int L, int D, int H,
+                                       int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, sp, seg)
+  if (i >= total) return;
+  const int seg = (int)(i & 7);
+  const long long pos = i >> 3;
+  const long long S = (long long)D * H * W;
+  const long long b = pos / S, sp = pos % S;
+  const int w = (int)(pos % W);
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  const int ww = w + seg - 1;
+  if (seg < 3 && ww >= 0 && ww < W) {
+    for (int co = 0; co < 8; ++co) f[co] = bpq[co];
+    for (int ci = 0; ci < L; ++ci) {
+      const float v = __fdiv_rn(z[((size_t)b * L + ci) * S + sp + (seg - 1)], scaling);
+      for (int co = 0; co < 8; ++co) f[co] += Wpq[co * L + ci] * v;
+    }
+  }
+  reinterpret_cast<uint4*>(out)[i] = f_to_h8(f);
+}
+void launch_pack_vae_dec_in(const float* z, const float* Wpq, const float* bpq, float scaling, __half* out, int B,
+                            int L, int D, int H, int W, cudaStream_t st) {
+  const long long total = (long long)B * D * H * W * 8;
+  pack_vae_dec_in_kernel<<<cdiv(total, 256), 256, 0, st>>>(z, Wpq, bpq, scaling, out, L, D, H, W, total);
+}
+
+// VAE encoder input: all 27 taps of the Cin-channel volume, slot = tap*Cin + ci, tap=(kd*3+kh)*3+kw
+__global__ void pack_vae_enc_in_kernel(const float* __restrict__ v, __half* out, int Cin, int Cpad, int D, int H,
+                                       int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, sp, seg)
+  if (i >= total) return;
+  const int nseg = Cpad / 8;
+  const int seg = (int)(i % nseg);
+  const long long pos = i / nseg;
+  const long long S = (long long)D * H * W;
+  const long long b = pos / S, sp = pos % S;
+  const int w = (int)(sp % W), h = (int)((sp / W) % H), d = (int)(sp / ((long long)W * H));
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int slot = seg * 8 + j;
+    const int tap = slot / Cin, ci = slot % Cin;
+    float x = 0.f;
+    if (tap < 27) {
+      const int dd = d + tap / 9 - 1, hh = h + (tap / 3) % 3 - 1, ww = w + tap % 3 - 1;
+      if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+        x = v[((size_t)b * Cin + ci) * S + ((size_t)dd * H + hh) * W + ww];
+    }
+    f[j] = x;
+  }
+  reinterpret_cast<uint4*>(out)[i] = f_to_h8(f);
+}
+void launch_pack_vae_enc_in(const float* v, __half* out, int B, int Cin, int Cpad, int D, int H, int W,
+                            cudaStream_t st) {
+  const long long total = (long long)B * D * H * W * (Cpad / 8);
+  pack_vae_enc_in_kernel<<<cdiv(total, 256), 256, 0, st>>>(v, out, Cin, Cpad, D, H, W, total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth-only trilinear resample of the conditioning latent (reference models/model.py:284-289:
+// F.interpolate(mode='trilinear', align_corners=False) with H, W unchanged), nc32 -> nc32.
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample_depth_kernel(const float* __restrict__ in, float* out, int Din, int Dout, long long HW,
+                                      long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (bc, dout, hw)
+  if (i >= total) return;
+  const long long hw = i % HW;
+  const int d = (int)((i / HW) % Dout);
+  const long long bc = i / (HW * Dout);
+  const float scale = (float)Din / (float)Dout;
+  float src = scale * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  const int d0 = (int)src;
+  const int d1 = d0 + ((d0 < Din - 1) ? 1 : 0);
+  const float l1 = src - (float)d0, l0 = 1.0f - l1;
+  const float* p = in + bc * Din * HW + hw;
+  out[i] = l0 * p[(size_t)d0 * HW] + l1 * p[(size_t)d1 * HW];
+}
+void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, long long HW, cudaStream_t st) {
+  const long long total = (long long)BC * Dout * HW;
+  upsample_depth_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out, Din, Dout, HW, total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout casts for the op-level API and tests
+// ------------------------------------------------------------------------------------------------
+__global__ void nc32_to_cl16_kernel(const float* __restrict__ in, __half* out, int C, int Cpad, long long S,
+                                    long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, sp, c)
+  if (i >= total) return;
+  const int c = (int)(i % Cpad);
+  const long long sp = (i / Cpad) % S, b = i / (Cpad * S);
+  out[i] = __float2half_rn(c < C ? in[((size_t)b * C + c) * S + sp] : 0.f);
+}
+__global__ void cl16_to_nc32_kernel(const __half* __restrict__ in, float* out, int C, int Cpad, long long S,
+                                    long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b, c, sp)
+  if (i >= total) return;
+  const long long sp = i % S;
+  const int c = (int)((i / S) % C);
+  const long long b = i / (S * C);
+  out[i] = __half2float(in[((size_t)b * S + sp) * Cpad + c]);
+}
+void launch_nc32_to_cl16(const float* in, __half* out, int B, int C, int Cpad, long long S, cudaStream_t st) {
+  const long long total = (long long)B * S * Cpad;
+  nc32_to_cl16_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out, C, Cpad, S, total);
+}
+void launch_cl16_to_nc32(const __half* in, float* out, int B, int C, int Cpad, long long S, cudaStream_t st) {
+  const long long total = (long long)B * S * C;
+  cl16_to_nc32_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, out, C, Cpad, S, total);
+}
+
+}  // namespace b2v

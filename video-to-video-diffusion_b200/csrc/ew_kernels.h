@@ -1,0 +1,36 @@
+// Launchers of the HBM-bound kernels (see ew_kernels.cu for what each one replaces in the reference).
+#pragma once
+#include "ptx.cuh"
+
+namespace b2v {
+
+void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const float* gamma, const float* beta,
+                     const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
+                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st);
+void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st);
+void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
+                      int T, int P, int C, int G, float eps, cudaStream_t st);
+void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, cudaStream_t st);
+void launch_temb(const long long* t_ptr, const long long* t_table, const int* step_ptr, const float* freqs,
+                 const float* W1, const float* b1, const float* W2, const float* b2, float* silu_temb,
+                 const float* Wp, const float* bp, float* proj, int rows, int dim, int td, int B, cudaStream_t st);
+void launch_ddim_update(float* z, const float* eps, const float* noise, const float* coef_table, const int* step_ptr,
+                        int step_imm, long long n, int* nan_flag, cudaStream_t st);
+struct Coef8 {
+  float v[8];
+};
+void launch_ddpm_update(float* z, const float* eps, const float* noise, const Coef8& coef, long long n,
+                        cudaStream_t st);
+void launch_advance_step(int* step, cudaStream_t st);
+void launch_set_t(long long* t_dev, const long long* t_table, const int* step, long long imm, int B, cudaStream_t st);
+void launch_pack_unet_in(const float* z, const float* c, __half* out, int B, int L, int D, int H, int W,
+                         cudaStream_t st);
+void launch_pack_vae_dec_in(const float* z, const float* Wpq, const float* bpq, float scaling, __half* out, int B,
+                            int L, int D, int H, int W, cudaStream_t st);
+void launch_pack_vae_enc_in(const float* v, __half* out, int B, int Cin, int Cpad, int D, int H, int W,
+                            cudaStream_t st);
+void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, long long HW, cudaStream_t st);
+void launch_nc32_to_cl16(const float* in, __half* out, int B, int C, int Cpad, long long S, cudaStream_t st);
+void launch_cl16_to_nc32(const __half* in, float* out, int B, int C, int Cpad, long long S, cudaStream_t st);
+
+}  // namespace b2v

@@ -1,0 +1,72 @@
+// U-Net denoiser object behind b2v_unet (see include/b2v.h)
+#pragma once
+#include "../../include/b2v.h"
+#include "engine.h"
+
+namespace b2v {
+
+struct ResW {  // ResBlock3D (models/unet3d.py:77-133)
+  ConvLayer conv1, conv2, res;
+  GNW n1, n2;
+  bool has_res = false;
+  int cin0 = 0, cin1 = 0, cout = 0;
+  int temb_off = 0;  // row offset of this block's time_mlp projection in the concatenated table
+};
+struct AttnW {  // TemporalAttention (models/unet3d.py:136-194), folded
+  GNW norm;
+  ConvLayer pv;
+  std::vector<float> u, bp;
+  int C = 0;
+};
+struct ULevel {
+  std::vector<ResW> res;
+  std::vector<AttnW> attn;
+  ConvLayer resample;
+  bool has_resample = false;
+};
+
+struct UProgram {
+  int B = 0, T = 0, h = 0, w = 0;
+  long long numel = 0;
+  DeviceStore ds;
+  Pool pool;
+  std::vector<Op> core;
+  Program fwd, ddim;
+  float *x_in = nullptr, *c_in = nullptr, *eps = nullptr;
+  long long *t_dev = nullptr, *t_table = nullptr;
+  int *step_dev = nullptr, *nan_dev = nullptr;
+  float *coef_table = nullptr, *stats = nullptr, *silu_temb = nullptr, *proj = nullptr;
+  size_t stats_cap = 0;
+};
+
+struct UNet {
+  b2v_unet_desc desc;
+  WeightMap wm;
+  bool finalized = false;
+  DeviceStore ds;
+  float *freqs = nullptr, *W1 = nullptr, *B1 = nullptr, *W2 = nullptr, *B2 = nullptr, *Wproj = nullptr,
+        *Bproj = nullptr;
+  int proj_rows = 0;
+  ConvLayer conv_in, conv_out;
+  GNW out_norm;
+  std::vector<ULevel> enc, dec;
+  ResW mid1, mid2;
+  AttnW mid_attn;
+  std::map<std::string, std::unique_ptr<UProgram>> progs;
+  UProgram* last = nullptr;
+  UProgram* active = nullptr;
+
+  int finalize();
+  UProgram* program(int B, int T, int h, int w);
+  int forward(const float* x, const long long* t, const float* c, float* eps_out, int B, int T, int h, int w,
+              cudaStream_t st);
+  int sampler_begin(const float* z_init, const float* cond, int B, int T, int h, int w, cudaStream_t st);
+  int ddim_sample(const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
+                  const long long* timesteps, int n, const float* ac, int n_train, float eta, const float* noise,
+                  int* nan_flag, cudaStream_t st);
+  int ddpm_step(long long t, const float* coef, const float* noise, cudaStream_t st);
+  int sampler_end(float* z_out, cudaStream_t st);
+  ~UNet();
+};
+
+}  // namespace b2v

@@ -1,0 +1,101 @@
+"""Op-level wrappers over the C ABI (building blocks + parity tests).  Activations are NDHWC fp16 ("cl16")."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+KIND_K3, KIND_K1, KIND_DOWN, KIND_UPT = 0, 1, 2, 3
+
+
+def to_cl16(x, cpad=None):
+    """(B,C,D,H,W) fp32 CUDA -> (B,D,H,W,Cpad) fp16"""
+    B, C, D, H, W = x.shape
+    cpad = cpad or C
+    out = torch.empty((B, D, H, W, cpad), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().b2v_nc32_to_cl16(_lib.dptr(x.contiguous()), _lib.dptr(out, torch.float16), B, C, cpad,
+                                           D * H * W, _lib.stream()), "nc32_to_cl16")
+    return out
+
+
+def from_cl16(x, C=None):
+    """(B,D,H,W,Cpad) fp16 -> (B,C,D,H,W) fp32"""
+    B, D, H, W, cpad = x.shape
+    C = C or cpad
+    out = torch.empty((B, C, D, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().b2v_cl16_to_nc32(_lib.dptr(x, torch.float16), _lib.dptr(out), B, C, cpad, D * H * W,
+                                           _lib.stream()), "cl16_to_nc32")
+    return out
+
+
+class Conv:
+    """One convolution layer on the tcgen05 implicit-GEMM kernel, built from torch-layout weights."""
+
+    def __init__(self, kind, weight, bias, cin0, cin1, cout):
+        self.kind, self.cin0, self.cin1, self.cout = kind, cin0, cin1, cout
+        w = weight.detach().to("cpu", torch.float32).contiguous()
+        b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().b2v_conv_create(ctypes.byref(h), kind, _lib.hptr(w), None if b is None else _lib.hptr(b),
+                                              cin0, cin1, cout), "conv_create")
+        self._h = h
+
+    def __call__(self, x0, x1=None, out_fp32=False, groups=0, tanh=False):
+        """x0/x1: cl16 (B,D,H,W,C).  Returns (out, stats): out cl16 or NCDHW fp32; stats (B,groups,2) or None."""
+        B, D, H, W, _ = x0.shape
+        oH, oW = (H // 2, W // 2) if self.kind == KIND_DOWN else (2 * H, 2 * W) if self.kind == KIND_UPT else (H, W)
+        if out_fp32:
+            out = torch.empty((B, self.cout, D, oH, oW), dtype=torch.float32, device=x0.device)
+        else:
+            out = torch.empty((B, D, oH, oW, self.cout), dtype=torch.float16, device=x0.device)
+        stats = torch.zeros((B, groups, 2), dtype=torch.float32, device=x0.device) if groups else None
+        _lib.check(_lib.lib().b2v_conv_forward(
+            self._h, _lib.dptr(x0, torch.float16), _lib.dptr(x1, torch.float16),
+            _lib.dptr(out, torch.float32 if out_fp32 else torch.float16), int(out_fp32), _lib.dptr(stats), groups,
+            int(tanh), B, D, H, W, _lib.stream()), "conv_forward")
+        return out, stats
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().b2v_conv_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def gn_apply(y, stats, gamma, beta, groups, temb=None, res=None, mode=0, groups_out=0):
+    """y: cl16 (B,D,H,W,C).  mode 0: silu(gn(y)) + temb ; mode 1: silu(gn(y) + res).  Returns (out, stats_out)."""
+    B, D, H, W, C = y.shape
+    out = torch.empty_like(y)
+    so = torch.zeros((B, groups_out, 2), dtype=torch.float32, device=y.device) if groups_out else None
+    _lib.check(_lib.lib().b2v_gn_apply(
+        _lib.dptr(y, torch.float16), _lib.dptr(out, torch.float16), _lib.dptr(stats), _lib.dptr(gamma), _lib.dptr(beta),
+        _lib.dptr(temb), _lib.dptr(res, torch.float16), B, D * H * W, C, groups, mode, _lib.dptr(so), groups_out,
+        _lib.stream()), "gn_apply")
+    return out, so
+
+
+def gn_stats(x, groups):
+    B, D, H, W, C = x.shape
+    st = torch.zeros((B, groups, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().b2v_gn_stats(_lib.dptr(x, torch.float16), B, D * H * W, C, groups, _lib.dptr(st),
+                                       _lib.stream()), "gn_stats")
+    return st
+
+
+def ddim_update(z, eps, coef, noise=None):
+    """in-place DDIM update of z (fp32); coef: device fp32[8].  Returns the NaN flag tensor."""
+    flag = torch.zeros(1, dtype=torch.int32, device=z.device)
+    _lib.check(_lib.lib().b2v_ddim_update(_lib.dptr(z), _lib.dptr(eps), _lib.dptr(noise), _lib.dptr(coef), z.numel(),
+                                          _lib.dptr(flag, torch.int32), _lib.stream()), "ddim_update")
+    return flag
+
+
+def upsample_depth(z, depth):
+    """F.interpolate(z, (depth, h, w), mode='trilinear', align_corners=False) for unchanged h, w"""
+    B, C, D, H, W = z.shape
+    out = torch.empty((B, C, depth, H, W), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.lib().b2v_upsample_depth(_lib.dptr(z.contiguous()), _lib.dptr(out), B * C, D, depth, H * W,
+                                             _lib.stream()), "upsample_depth")
+    return out
