@@ -104,6 +104,12 @@ int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, i
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream);
 int b2v_vae_profile(b2v_vae* v, int which /*0 encode, 1 decode*/, int iters, char* buf, size_t cap, void* stream);
 
+/* debugging / bisecting: (re)run the first n_ops ops of the last planned program eagerly, then copy the primary
+ * output of op `index` (device -> dst, a DEVICE buffer of cap bytes); returns the byte count, <0 on error.
+ * prog: 0 = U-Net forward | 1 = VAE encode | 2 = VAE decode.  b2v_debug_op_name returns "" past the end.    */
+long long b2v_debug_op_output(void* obj, int prog, int n_ops, int index, void* dst, size_t cap, void* stream);
+const char* b2v_debug_op_name(void* obj, int prog, int index);
+
 /* ---------------------------------------------------------------- op level (parity tests, building blocks) --
  * activations here are NDHWC fp16 ("cl16") device buffers                                                     */
 typedef struct b2v_conv b2v_conv;

@@ -1,0 +1,227 @@
+"""Model-level parity on the B200, through the mirror classes and the C ABI:
+  * against the golden vectors of the unmodified reference (tests/golden, tiny configs),
+  * against the oracle (oracle/ref_port.py) run in true fp32 on the same GPU at BASELINE.json's full shapes,
+  * teacher-forced per-step eps rel-L2 <= 1e-2 and final-volume PSNR within 0.05 dB (north_star tolerances).
+"""
+import pytest
+import torch
+
+from helpers import TINY_UNET, golden, rel_l2, tiny_unet, tiny_vae
+from oracle import ref_port as R
+
+pytestmark = pytest.mark.gpu
+EPS_TOL = 1e-2  # north_star: per-step noise-prediction relative L2 (fp16 operands, fp32 accumulate)
+
+
+def _sd(m, dev):
+    return {k: v.to(dev) for k, v in m.state_dict().items()}
+
+
+def test_unet_forward_golden_and_oracle(cuda_dev):
+    g = golden("unet_tiny.pt")
+    m = tiny_unet(g["seed"]).to(cuda_dev)
+    eps = m(g["x"].to(cuda_dev), g["t"].to(cuda_dev), g["c"].to(cuda_dev))
+    assert eps.shape == g["eps"].shape and eps.dtype == torch.float32
+    assert rel_l2(eps.cpu(), g["eps"]) < EPS_TOL, rel_l2(eps.cpu(), g["eps"])
+    with torch.no_grad():
+        ref = R.unet_forward(_sd(m, cuda_dev), TINY_UNET, g["x"].to(cuda_dev), g["t"].to(cuda_dev), g["c"].to(cuda_dev))
+    assert rel_l2(eps, ref) < EPS_TOL
+    # replaying the captured graph gives the same answer, and samples of a batch do not interact.  Not bitwise:
+    # GroupNorm statistics are accumulated with fp32 atomics (order varies, ~1e-7) and fp16 storage rounding
+    # amplifies any perturbation towards the fp16 floor (~1e-3) over depth -- see DESIGN.md "Reproducibility".
+    eps2 = m(g["x"].to(cuda_dev), g["t"].to(cuda_dev), g["c"].to(cuda_dev))
+    assert rel_l2(eps2, eps) < 5e-3
+    one = m(g["x"][:1].to(cuda_dev), g["t"][:1].to(cuda_dev), g["c"][:1].to(cuda_dev))
+    assert rel_l2(one, eps[:1]) < 5e-3
+
+
+def test_unet_rejects_cpu_input():
+    m = tiny_unet(0)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 4, 8, 8), torch.zeros(1, dtype=torch.long), torch.zeros(1, 4, 4, 8, 8))
+
+
+def test_vae_golden(cuda_dev):
+    g = golden("vae_tiny.pt")
+    vae = tiny_vae(g["seed"]).to(cuda_dev)
+    z = vae.encode(g["v"].to(cuda_dev))
+    rec = vae.decode(g["z"].to(cuda_dev))
+    assert z.shape == g["z"].shape and rec.shape == g["recon"].shape
+    assert rel_l2(z.cpu(), g["z"]) < EPS_TOL, rel_l2(z.cpu(), g["z"])
+    assert rel_l2(rec.cpu(), g["recon"]) < EPS_TOL, rel_l2(rec.cpu(), g["recon"])
+    rec2, z2 = vae(g["v"].to(cuda_dev))
+    assert rel_l2(z2, z) < 5e-3 and rec2.shape == rec.shape
+
+
+def test_ddim_teacher_forced_and_final(cuda_dev):
+    from v2v_b200.inference import DDIMSampler
+    from v2v_b200.models import GaussianDiffusion
+    g = golden("ddim_tiny.pt")
+    m = tiny_unet(0).to(cuda_dev)
+    cond = g["cond"].to(cuda_dev)
+    worst = 0.0
+    for s in g["steps"]:  # teacher-forced on the reference's own trajectory
+        e = m(s["z"].to(cuda_dev), torch.tensor([s["t"]], device=cuda_dev), cond)
+        worst = max(worst, rel_l2(e.cpu(), s["eps"]))
+    assert worst < EPS_TOL, worst
+    diff = GaussianDiffusion("cosine", 1000).to(cuda_dev)
+    smp = DDIMSampler(diff, m)
+    assert smp._get_timesteps(5).tolist() == [999, 800, 600, 400, 200, 0]
+    # free-running loop from the reference's initial noise (CPU and CUDA randn streams differ, so inject it)
+    z0 = g["steps"][0]["z"].to(cuda_dev)
+    orig = torch.randn
+    try:
+        torch.randn = lambda *a, **k: z0.clone()
+        z = smp.sample((1, 4, 4, 8, 8), cond, 5, cuda_dev, progress=False)
+    finally:
+        torch.randn = orig
+    assert rel_l2(z.cpu(), g["z_final"]) < 5e-2, rel_l2(z.cpu(), g["z_final"])
+    assert smp.last_nan_flag.item() == 0
+
+
+def test_ddim_loop_equals_oracle_loop_on_gpu(cuda_dev):
+    """same seed on the same device => same noise stream as the oracle's (reference-ordered) draws, eta 0 and > 0"""
+    from v2v_b200.inference import DDIMSampler
+    from v2v_b200.models import GaussianDiffusion
+    m = tiny_unet(0).to(cuda_dev)
+    sd = _sd(m, cuda_dev)
+    cond = golden("ddim_tiny.pt")["cond"].to(cuda_dev)
+    model = lambda z, t, c: R.unet_forward(sd, TINY_UNET, z, t, c)  # noqa: E731
+    buf = R.diffusion_buffers("cosine", 1000)
+    diff = GaussianDiffusion("cosine", 1000).to(cuda_dev)
+    for eta in (0.0, 0.5):
+        torch.manual_seed(7)
+        with torch.no_grad():
+            ref = R.ddim_sample(model, buf, (1, 4, 4, 8, 8), cond, 5, cuda_dev, eta=eta)
+        torch.manual_seed(7)
+        got = DDIMSampler(diff, m).sample((1, 4, 4, 8, 8), cond, 5, cuda_dev, eta=eta, progress=False)
+        assert rel_l2(got, ref) < 5e-2, (eta, rel_l2(got, ref))
+
+
+def test_ddim_generic_model_path(cuda_dev):
+    """DDIMSampler accepts any callable model (as the reference does); the update still runs on our kernel"""
+    from v2v_b200.inference import DDIMSampler
+    from v2v_b200.models import GaussianDiffusion
+    diff = GaussianDiffusion("cosine", 1000)
+    cond = torch.zeros((1, 4, 2, 4, 4), device=cuda_dev)
+    fake = lambda z, t, c: 0.5 * z  # noqa: E731
+    torch.manual_seed(3)
+    got = DDIMSampler(diff, fake).sample((1, 4, 2, 4, 4), cond, 4, cuda_dev, progress=False)
+    torch.manual_seed(3)
+    ref = R.ddim_sample(fake, R.diffusion_buffers("cosine", 1000), (1, 4, 2, 4, 4), cond, 4, cuda_dev)
+    assert torch.equal(got, ref)  # fp32 update is bit-exact against the reference formula
+
+
+def test_ddpm_short_schedule(cuda_dev):
+    from v2v_b200.inference import DDPMSampler
+    from v2v_b200.models import GaussianDiffusion
+    m = tiny_unet(0).to(cuda_dev)
+    sd = _sd(m, cuda_dev)
+    cond = golden("ddpm_tiny.pt")["cond"].to(cuda_dev)
+    model = lambda z, t, c: R.unet_forward(sd, TINY_UNET, z, t, c)  # noqa: E731
+    torch.manual_seed(9)
+    with torch.no_grad():
+        ref = R.ddpm_sample(model, R.diffusion_buffers("cosine", 12), (1, 4, 4, 8, 8), cond, cuda_dev)
+    torch.manual_seed(9)
+    got = DDPMSampler(GaussianDiffusion("cosine", 12).to(cuda_dev), m).sample((1, 4, 4, 8, 8), cond, cuda_dev,
+                                                                              progress=False)
+    assert rel_l2(got, ref) < 3e-2, rel_l2(got, ref)
+
+
+def test_generate_tiny_against_reference_golden(cuda_dev):
+    from v2v_b200.models import VideoToVideoDiffusion
+    g = golden("generate_tiny.pt")
+    torch.manual_seed(g["seed"])
+    m = VideoToVideoDiffusion(g["config"]).eval().to(cuda_dev)
+    # oracle on the GPU with the same seed = the reference's RNG order on this device
+    torch.manual_seed(g["sample_seed"])
+    with torch.no_grad():
+        ref = R.generate(_sd(m, cuda_dev), g["config"], g["v_in"].to(cuda_dev), "ddim", g["steps"],
+                         target_depth=g["target_depth"])
+    torch.manual_seed(g["sample_seed"])
+    got = m.generate(g["v_in"].to(cuda_dev), "ddim", g["steps"], target_depth=g["target_depth"])
+    assert got.shape == g["v_out"].shape
+    # free-running through the reference's x0 clamp (+-10 after a x9880 division at t=999) is chaotic, so this is
+    # a loose end-to-end sanity bound; the strict gates are the teacher-forced steps and the PSNR test below
+    assert rel_l2(got, ref) < 0.2, rel_l2(got, ref)
+    n = lambda v: (v.clamp(-1, 1) + 1) / 2  # noqa: E731
+    assert R.psnr(n(got), n(ref)) > 25.0
+    with pytest.raises(ValueError):
+        m.generate(g["v_in"].to(cuda_dev), "euler")
+
+
+# ------------------------------------------------------------------------------------- BASELINE.json shapes
+@pytest.fixture(scope="module")
+def bench_model(cuda_dev):
+    import os
+    import yaml
+    from v2v_b200.models import VideoToVideoDiffusion
+    cfg = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "golden", "slice_interpolation_full_medium.yaml")))
+    torch.manual_seed(0)
+    m = VideoToVideoDiffusion(cfg).eval().to(cuda_dev)
+    return m, cfg
+
+
+@pytest.mark.timeout(600)
+def test_full_unet_step_vs_fp32_oracle(cuda_dev, bench_model):
+    """config 1 shape: latent (1,8,48,48,48); per-step eps rel-L2 <= 1e-2 at early / middle / late timesteps"""
+    m, cfg = bench_model
+    _, unet_cfg, _ = R.resolve_config(cfg)
+    sd = {k[len("unet."):]: v for k, v in m.state_dict().items() if k.startswith("unet.")}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((1, 8, 48, 48, 48), generator=g).to(cuda_dev)
+    c = torch.randn((1, 8, 48, 48, 48), generator=g).to(cuda_dev)
+    for tv in (999, 500, 0):
+        t = torch.tensor([tv], device=cuda_dev)
+        got = m.unet(x, t, c)
+        with torch.no_grad():
+            ref = R.unet_forward(sd, unet_cfg, x, t, c)
+        err = rel_l2(got, ref)
+        print(f"full U-Net step t={tv}: rel-L2 = {err:.3e}")
+        assert err < EPS_TOL, (tv, err)
+
+
+@pytest.mark.timeout(600)
+def test_full_vae_decode_and_encode_vs_fp32_oracle(cuda_dev, bench_model):
+    m, cfg = bench_model
+    sd = {k[len("vae."):]: v for k, v in m.state_dict().items() if k.startswith("vae.")}
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn((1, 8, 48, 48, 48), generator=g).to(cuda_dev)
+    got = m.vae.decode(z)
+    with torch.no_grad():
+        ref = R.vae_decode(sd, z, 1.0)
+    assert got.shape == (1, 1, 48, 192, 192)
+    err = rel_l2(got, ref)
+    psnr = R.psnr((got.clamp(-1, 1) + 1) / 2, (ref.clamp(-1, 1) + 1) / 2)
+    print(f"VAE decode: rel-L2 = {err:.3e}, PSNR(new, ref) = {psnr:.1f} dB")
+    assert err < EPS_TOL, err
+    del ref
+    v = (torch.rand((1, 1, 8, 192, 192), generator=g) * 2 - 1).to(cuda_dev)
+    ze = m.vae.encode(v)
+    with torch.no_grad():
+        zr = R.vae_encode(sd, v, 1.0)
+    assert ze.shape == (1, 8, 8, 48, 48)
+    assert rel_l2(ze, zr) < EPS_TOL, rel_l2(ze, zr)
+
+
+@pytest.mark.timeout(1200)
+def test_full_generate_ddim50_psnr_gate(cuda_dev, bench_model):
+    """BASELINE config 1 end to end: (1,1,8,192,192) -> (1,1,48,192,192), DDIM-50 (51 evaluations).
+    Gate: |PSNR(new, target) - PSNR(ref_fp32, target)| <= 0.05 dB on a synthetic target;
+    direct PSNR(new, ref) is reported."""
+    m, cfg = bench_model
+    sd = _sd(m, cuda_dev)
+    g = torch.Generator().manual_seed(1234)
+    v_thick = (torch.rand((1, 1, 8, 192, 192), generator=g) * 2 - 1).to(cuda_dev)
+    target = (torch.rand((1, 1, 48, 192, 192), generator=g) * 2 - 1).to(cuda_dev)
+    torch.manual_seed(42)
+    got = m.generate(v_thick, "ddim", 50, target_depth=48)
+    torch.manual_seed(42)
+    with torch.no_grad():
+        ref = R.generate(sd, cfg, v_thick, "ddim", 50, target_depth=48)
+    assert got.shape == ref.shape == (1, 1, 48, 192, 192)
+    n = lambda v: (v.clamp(-1, 1) + 1) / 2  # noqa: E731
+    p_new, p_ref, p_direct = R.psnr(n(got), n(target)), R.psnr(n(ref), n(target)), R.psnr(n(got), n(ref))
+    print(f"generate DDIM-50: PSNR(new,target)={p_new:.4f} PSNR(ref,target)={p_ref:.4f} PSNR(new,ref)={p_direct:.2f} dB")
+    assert abs(p_new - p_ref) <= 0.05, (p_new, p_ref)
+    assert torch.isfinite(got).all()

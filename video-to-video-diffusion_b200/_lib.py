@@ -56,6 +56,8 @@ SIGNATURES = {
     "b2v_upsample_depth": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "b2v_unet_profile": (c_int, [_P, c_int, c_char_p, c_size_t, _P]),
     "b2v_vae_profile": (c_int, [_P, c_int, c_int, c_char_p, c_size_t, _P]),
+    "b2v_debug_op_output": (c_longlong, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "b2v_debug_op_name": (c_char_p, [_P, c_int, c_int]),
     "b2v_conv_create": (c_int, [POINTER(_P), c_int, _P, _P, c_int, c_int, c_int]),
     "b2v_conv_destroy": (None, [_P]),
     "b2v_conv_forward": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

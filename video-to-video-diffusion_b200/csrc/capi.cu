@@ -119,6 +119,33 @@ int b2v_vae_profile(b2v_vae* v, int which, int iters, char* buf, size_t cap, voi
   return write_json(js, buf, cap);
 }
 
+static Program* debug_prog(void* obj, int prog) {
+  if (prog == 0) {
+    UNet& u = ((b2v_unet*)obj)->u;
+    return u.last ? &u.last->fwd : nullptr;
+  }
+  VAE& v = ((b2v_vae*)obj)->v;
+  return v.last[prog - 1] ? &v.last[prog - 1]->prog : nullptr;
+}
+long long b2v_debug_op_output(void* obj, int prog, int n_ops, int index, void* dst, size_t cap, void* stream) {
+  Program* P = debug_prog(obj, prog);
+  if (!P) return fail("debug: run the program once first");
+  if (index < 0 || index >= (int)P->ops.size() || index >= n_ops) return fail("debug: bad op index");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_ops && i < (int)P->ops.size(); ++i) P->ops[i].run(st);
+  const Op& op = P->ops[index];
+  if (!op.out) return 0;
+  const size_t n = op.out_bytes < cap ? op.out_bytes : cap;
+  B2V_CUDA(cudaMemcpyAsync(dst, op.out, n, cudaMemcpyDeviceToDevice, st));
+  B2V_CUDA(cudaStreamSynchronize(st));
+  return (long long)n;
+}
+const char* b2v_debug_op_name(void* obj, int prog, int index) {
+  Program* P = debug_prog(obj, prog);
+  if (!P || index < 0 || index >= (int)P->ops.size()) return "";
+  return P->ops[index].name.c_str();
+}
+
 // ------------------------------------------------------------------ glue / op level
 int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, int HW, void* stream) {
   if (check_device()) return -1;

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           if (p.cpg >= 32) chunk_stats<32>(v, ncol, valid, srow, gbase, lane);
           else if (p.cpg == 16) chunk_stats<16>(v, ncol, valid, srow, gbase, lane);
           else if (p.cpg == 8) chunk_stats<8>(v, ncol, valid, srow, gbase, lane);
-          else chunk_stats<4>(v, ncol, valid, srow, gbase, lane);
+          else if (p.cpg == 4) chunk_stats<4>(v, ncol, valid, srow, gbase, lane);
+          else chunk_stats<2>(v, ncol, valid, srow, gbase, lane);
         }
         if (p.act == ACT_TANH) {
 #pragma unroll

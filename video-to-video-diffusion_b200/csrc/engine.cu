@@ -1,6 +1,7 @@
 #include "engine.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace b2v {
 
@@ -86,6 +87,12 @@ int Program::run_eager(cudaStream_t st) {
 }
 
 int Program::run(cudaStream_t st) {
+  static const bool eager = getenv("B2V_EAGER") != nullptr;  // debugging aid: plain launches instead of a graph
+  if (eager) {
+    if (!launches)
+      for (auto& op : ops) launches += op.launches;
+    return run_eager(st);
+  }
   if (!exec) {
     launches = 0;
     for (auto& op : ops) launches += op.launches;
@@ -228,6 +235,8 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
   op.name = name;
   op.flops = P.flops;
   op.bytes = 0;
+  op.out = out_fp32 ? (void*)out_fp32 : (void*)out.p;
+  op.out_bytes = out_fp32 ? (size_t)B * L.cout * oD * oH * oW * 4 : (size_t)B * oD * oH * oW * L.cout * 2;
   op.run = [P](cudaStream_t st) { conv_launch(P, st); };
   ops.push_back(std::move(op));
   return out;
@@ -245,6 +254,8 @@ void Builder::gn_apply(const std::string& name, Act& y, const float* stats_in, c
   Op op;
   op.name = name;
   op.bytes = (double)Bc * S * C * 2.0 * (res ? 3.0 : 2.0);
+  op.out = yp;
+  op.out_bytes = (size_t)Bc * S * C * 2;
   op.run = [=](cudaStream_t st) {
     launch_gn_apply(yp, yp, stats_in, ga, be, temb, temb_stride, rp, Bc, S, C, G, 1e-5f, mode, stats_out, G_out, st);
   };

@@ -62,6 +62,8 @@ struct Op {
   std::string name;
   double flops = 0, bytes = 0;
   int launches = 1;
+  void* out = nullptr;      // primary output of the op (debug / bisecting)
+  size_t out_bytes = 0;
   std::function<void(cudaStream_t)> run;
 };
 

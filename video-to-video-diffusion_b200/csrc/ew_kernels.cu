@@ -41,7 +41,7 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
 // stats_in : [B][G][2] raw (sum, sumsq) over S*cpg elements, produced by the conv epilogue.
 // Grid: (blocks, B); block = C8*R threads, each thread owns 8 fixed channels and strides over rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_apply_kernel(const __half* __restrict__ y_, __half* out_, const float* __restrict__ stats_in,
+__global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __restrict__ stats_in,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ temb, int temb_stride, const __half* res_, long long S,
                                 int C, int G, float eps, int mode, float* stats_out, int G_out) {
