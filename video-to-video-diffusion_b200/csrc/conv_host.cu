@@ -265,8 +265,8 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
   p.stats = stats;
   p.groups = groups;
   p.cpg = groups ? L.cout / groups : 1;
-  if (stats && (p.cpg < 2 || (p.cpg & (p.cpg - 1)))) {
-    err = "conv_plan: channels per group must be a power of two >= 2";
+  if (stats && (p.cpg < 2 || (p.cpg & (p.cpg - 1)) || (L.bn + p.cpg - 1) / p.cpg > 64)) {
+    err = "conv_plan: channels per group must be a power of two >= 2 (and <= 64 groups per N tile)";
     return -1;
   }
   p.cout_valid = L.cout;

@@ -48,29 +48,52 @@ struct ConvCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*group stats*/;
 };
 
-template <int SUB>
-__device__ __forceinline__ void chunk_stats(const float* v, int ncol, bool valid, float* srow, int gbase, int lane) {
+// Sum N per-lane values across the 32 lanes of a warp with N-1 + log2(32/N) shuffles (instead of 5 per value):
+// at every stage half of the values travel to the partner lane.  Returns the total of value `idx`
+// = top log2(N) bits of the lane id; all lanes of one idx class hold the same result.
+template <int N>
+__device__ __forceinline__ float multi_reduce(float (&v)[N], int lane) {
+  constexpr int LOG = (N == 32) ? 5 : (N == 16) ? 4 : (N == 8) ? 3 : (N == 4) ? 2 : 1;
 #pragma unroll
-  for (int seg = 0; seg < 32 / SUB; ++seg) {
-    if (seg * SUB < ncol) {
-      float s = 0.f, ss = 0.f;
+  for (int s = 0; s < LOG; ++s) {
+    const int off = 16 >> s;
+    const int n = N >> s;
+    const bool up = (lane & off) != 0;
 #pragma unroll
-      for (int j = 0; j < SUB; ++j) {
-        float x = valid ? v[seg * SUB + j] : 0.f;
-        s += x;
-        ss += x * x;
-      }
-      s = warp_sum(s);
-      ss = warp_sum(ss);
-      if (lane == 0) {
-        atomicAdd(srow + (gbase + seg) * 2, s);
-        atomicAdd(srow + (gbase + seg) * 2 + 1, ss);
-      }
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = up ? v[j] : v[j + n / 2];
+      const float keep = up ? v[j + n / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
+#pragma unroll
+  for (int off = (16 >> LOG); off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// per-(sample, group) sum / sum-of-squares of one 32-column chunk, accumulated into the CTA's shared-memory
+// table (flushed to global memory with one atomic per group when the CTA moves to another sample / n-tile)
+template <int SUB>  // columns per group inside the chunk: min(channels-per-group, 32)
+__device__ __forceinline__ void chunk_stats(const float* v, bool valid, float* sstat, int glocal, int lane) {
+  constexpr int SEGS = 32 / SUB, N = 2 * SEGS, LOG = (N == 32) ? 5 : (N == 16) ? 4 : (N == 8) ? 3 : (N == 4) ? 2 : 1;
+  float acc[N];
+#pragma unroll
+  for (int seg = 0; seg < SEGS; ++seg) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < SUB; ++j) {
+      const float x = valid ? v[seg * SUB + j] : 0.f;
+      s += x;
+      ss += x * x;
+    }
+    acc[2 * seg] = s;
+    acc[2 * seg + 1] = ss;
+  }
+  const float tot = multi_reduce<N>(acc, lane);
+  if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(&sstat[glocal * 2 + (lane >> (5 - LOG))], tot);
 }
 
 template <int BN>
@@ -86,6 +109,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // [<=128 groups][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +132,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TM_COLS);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,6 +217,20 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     const int rw = r % p.bw;
     const int rh = (r / p.bw) % p.bh;
     const int rd = r / (p.bw * p.bh);
+    const int et = threadIdx.x - 64;           // 0..127 within the epilogue warps
+    const int ng = (BN + p.cpg - 1) / p.cpg;   // groups touched by one n-tile
+    int cur_key = -1, cur_nb = 0, cur_g0 = 0;
+    // flush the CTA-local group statistics: one global atomic per (group, moment)
+    auto flush = [&]() {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < 2 * ng) {
+        const float val = sstat[et];
+        sstat[et] = 0.f;
+        const int g = cur_g0 + (et >> 1);
+        if (g < p.groups) atomicAdd(p.stats + ((size_t)cur_nb * p.groups + g) * 2 + (et & 1), val);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -208,7 +247,15 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       const int nb = m / p.tiles_d;
       const bool valid = (r < p.rows_valid) && (w < p.W) && (h < p.H) && (d < p.D);
       const long long roff = p.cls_off[cls] + nb * p.sN + d * p.sD + h * p.sH + w * p.sW;
-      float* srow = p.stats ? (p.stats + (size_t)nb * p.groups * 2) : nullptr;
+      if (p.stats) {
+        const int key = nb * p.n_tiles + n0 / BN;
+        if (key != cur_key) {
+          if (cur_key >= 0) flush();
+          cur_key = key;
+          cur_nb = nb;
+          cur_g0 = n0 / p.cpg;
+        }
+      }
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -225,14 +272,15 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         if (cg >= p.cout_valid) break;
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + cg + j);
-        if (srow) {
-          const int gbase = cg / p.cpg;
-          const int ncol = min(CH, p.cout_valid - cg);
-          if (p.cpg >= 32) chunk_stats<32>(v, ncol, valid, srow, gbase, lane);
-          else if (p.cpg == 16) chunk_stats<16>(v, ncol, valid, srow, gbase, lane);
-          else if (p.cpg == 8) chunk_stats<8>(v, ncol, valid, srow, gbase, lane);
-          else if (p.cpg == 4) chunk_stats<4>(v, ncol, valid, srow, gbase, lane);
-          else chunk_stats<2>(v, ncol, valid, srow, gbase, lane);
+        if constexpr (CH == 32) {
+          if (p.stats) {
+            const int gl = cg / p.cpg - cur_g0;
+            if (p.cpg >= 32) chunk_stats<32>(v, valid, sstat, gl, lane);
+            else if (p.cpg == 16) chunk_stats<16>(v, valid, sstat, gl, lane);
+            else if (p.cpg == 8) chunk_stats<8>(v, valid, sstat, gl, lane);
+            else if (p.cpg == 4) chunk_stats<4>(v, valid, sstat, gl, lane);
+            else chunk_stats<2>(v, valid, sstat, gl, lane);
+          }
         }
         if (p.act == ACT_TANH) {
 #pragma unroll
@@ -266,6 +314,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (p.stats && cur_key >= 0) flush();
   }
 
   tc_fence_before();

@@ -10,7 +10,15 @@ namespace b2v {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU op (tanh.approx, |err| <= 2^-11 relative, i.e. below
+// the fp16 rounding of the stored result) instead of ex2 + IEEE division -- the apply kernels were issue-bound on it
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-x)); }
 
 struct H8 {
   uint4 u;
@@ -79,33 +87,52 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
   uint4* out = reinterpret_cast<uint4*>(out_ + base);
   const uint4* res = res_ ? reinterpret_cast<const uint4*>(res_ + base) : nullptr;
 
-  for (long long row = (long long)blockIdx.x * R + rr; row < S; row += (long long)gridDim.x * R) {
-    const size_t idx = (size_t)row * C8 + cv;
-    float f[8];
-    h8_to_f(y[idx], f);
-    if (mode == 0) {
+  // 4 rows per iteration: all loads are issued before the first use so each thread keeps 4-8 16-byte requests
+  // in flight (the kernel is HBM-bound; one request per thread leaves the memory system latency-limited)
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * R;
+  for (long long row0 = (long long)blockIdx.x * R + rr; row0 < S; row0 += U * stride) {
+    uint4 yv[U], rv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j]) + ta[j];
-    } else {
-      float rf[8];
-      if (res) {
-        h8_to_f(res[idx], rf);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rf[j] = 0.f;
+    for (int k = 0; k < U; ++k) {
+      const long long row = row0 + k * stride;
+      if (row < S) {
+        const size_t idx = (size_t)row * C8 + cv;
+        yv[k] = y[idx];
+        if (mode == 1 && res) rv[k] = res[idx];
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j] + rf[j]);
     }
-    const uint4 o = f_to_h8(f);
-    out[idx] = o;
-    if (stats_out) {
-      float g[8];
-      h8_to_f(o, g);  // statistics of the values the consumer will actually read
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        as[j] += g[j];
-        ass[j] += g[j] * g[j];
+    for (int k = 0; k < U; ++k) {
+      const long long row = row0 + k * stride;
+      if (row >= S) break;
+      const size_t idx = (size_t)row * C8 + cv;
+      float f[8];
+      h8_to_f(yv[k], f);
+      if (mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j]) + ta[j];
+      } else {
+        float rf[8];
+        if (res) {
+          h8_to_f(rv[k], rf);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rf[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j] + rf[j]);
+      }
+      const uint4 o = f_to_h8(f);
+      out[idx] = o;
+      if (stats_out) {
+        float g[8];
+        h8_to_f(o, g);  // statistics of the values the consumer will actually read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          as[j] += g[j];
+          ass[j] += g[j] * g[j];
+        }
       }
     }
   }
@@ -137,7 +164,7 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
   const int threads = C8 * R;
-  long long want = (S + R - 1) / R;
+  long long want = (S + 4 * R - 1) / (4 * R);
   long long cap = (148LL * 8 + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
@@ -296,14 +323,14 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ t_ptr, const long 
     float acc = 0.f;
     for (int k = lane; k < dim; k += 32) acc += W1[(size_t)r * dim + k] * emb[k];
     acc = warp_sum(acc);
-    if (lane == 0) h1[r] = silu_f(acc + b1[r]);
+    if (lane == 0) h1[r] = silu_exact(acc + b1[r]);
   }
   __syncthreads();
   for (int r = warp; r < td; r += nw) {
     float acc = 0.f;
     for (int k = lane; k < td; k += 32) acc += W2[(size_t)r * td + k] * h1[k];
     acc = warp_sum(acc);
-    if (lane == 0) silu_temb[(size_t)b * td + r] = silu_f(acc + b2[r]);
+    if (lane == 0) silu_temb[(size_t)b * td + r] = silu_exact(acc + b2[r]);
   }
 }
 
