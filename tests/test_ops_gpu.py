@@ -58,8 +58,9 @@ def _weight(kind, cin, cout, g):
     return torch.randn(shape, generator=g) / fan ** 0.5
 
 
+@pytest.mark.parametrize("groups", [8, 32])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_vs_torch(cuda_dev, case):
+def test_conv_vs_torch(cuda_dev, case, groups):
     from v2v_b200 import ops
     name, kind, cin0, cin1, cout, N, D, H, W = case
     g = torch.Generator().manual_seed(hash(name) % 1000)
@@ -70,7 +71,6 @@ def test_conv_vs_torch(cuda_dev, case):
     conv = ops.Conv(kind, w, b, cin0, cin1, cout)
     x0 = ops.to_cl16(x[:, :cin0].contiguous())
     x1 = ops.to_cl16(x[:, cin0:].contiguous()) if cin1 else None
-    groups = 8
     out, stats = conv(x0, x1, groups=groups)
     torch.cuda.synchronize()
     got = ops.from_cl16(out)

@@ -1,6 +1,9 @@
 #include "conv_host.h"
 
+#include "conv_igemm_t.cuh"
+
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -65,6 +68,8 @@ int conv_setup_kernels(std::string& err) {
     e = cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::SMEM);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<256>::SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
   if (e != cudaSuccess) {
     err = std::string("cudaFuncSetAttribute(conv_igemm): ") + cudaGetErrorString(e);
     return -1;
@@ -319,8 +324,13 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) p.cls_off[ph * 2 + pw] = ph * oW + pw;
   }
-  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N * p.nclass * p.n_tiles;
+  long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N * p.nclass * p.n_tiles;
   const int sms = device_sm_count();
+  static const bool no_swap = getenv("B2V_NO_SWAP") != nullptr;
+  const int tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
+  P.swapped = !no_swap && L.cout == 128 && L.bn == 128 && out_mode == OUT_CL16 && act == ACT_NONE &&
+              (tiles_per_sample % 2 == 0) && (!stats || p.cpg <= 32);
+  if (P.swapped) total /= 2;
   P.grid = (int)(total < sms ? total : sms);
   const double taps_real = (L.kind == CONV_K1) ? 1 : (L.kind == CONV_DOWN || L.kind == CONV_UPT) ? 48 : 27;
   const double pos = (L.kind == CONV_UPT) ? (double)N * D * H * W : (double)N * gD * gH * gW;
@@ -329,6 +339,10 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
 }
 
 void conv_launch(const ConvPlan& P, cudaStream_t st) {
+  if (P.swapped) {
+    conv_igemm_t_kernel<<<P.grid, 192, ConvCfgT::SMEM, st>>>(P.p);
+    return;
+  }
   switch (P.bn) {
     case 16: conv_igemm_kernel<16><<<P.grid, 192, ConvCfg<16>::SMEM, st>>>(P.p); break;
     case 64: conv_igemm_kernel<64><<<P.grid, 192, ConvCfg<64>::SMEM, st>>>(P.p); break;

@@ -2,7 +2,10 @@
 #pragma once
 #include <string>
 
-#include "conv_igemm.cuh"
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "conv_params.h"
 
 namespace b2v {
 
@@ -31,6 +34,7 @@ struct ConvPlan {
   ConvParams p;
   int bn = 0;
   int grid = 0;
+  bool swapped = false;  // Cout == 128: operand-swapped kernel (conv_igemm_t.cuh)
   double flops = 0;  // algorithmic 2*MAC of the reference convolution (no padding / packing waste)
 };
 

@@ -17,29 +17,10 @@
 // Strided (1,2,2) convs read four parity views of the input (four tensor maps with doubled strides);
 // transposed (1,2,2) convs run as four output-parity classes of 3x2x2 taps each.
 #pragma once
+#include "conv_params.h"
 #include "ptx.cuh"
 
 namespace b2v {
-
-enum { OUT_CL16 = 0, OUT_F32 = 1 };
-enum { ACT_NONE = 0, ACT_TANH = 1 };
-
-struct ConvParams {
-  CUtensorMap tmA[4];
-  CUtensorMap tmB;
-  int32_t taps[48];       // per (class, tap): (map << 24) | ((dd+8) << 16) | ((dh+8) << 8) | (dw+8)
-  long long cls_off[4];   // output element offset of each class
-  long long sN, sD, sH, sW, sC;  // output strides (elements)
-  void* out;
-  const float* bias;      // [n_tiles*BN]
-  float* stats;           // [batch][groups][2] (sum, sumsq) or nullptr
-  int bw, bh, bd, rows_valid;
-  int tiles_w, tiles_h, tiles_d, batch;
-  int n_tiles, nclass, ntaps;
-  int src_chunks0, src_chunks1;
-  int W, H, D;            // logical grid of output positions per sample and class
-  int groups, cpg, cout_valid, out_mode, act;
-};
 
 template <int BN>
 struct ConvCfg {

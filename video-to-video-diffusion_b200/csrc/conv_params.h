@@ -1,0 +1,28 @@
+// Kernel parameter block shared by the implicit-GEMM convolution kernels and their host-side planner.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace b2v {
+
+enum { OUT_CL16 = 0, OUT_F32 = 1 };
+enum { ACT_NONE = 0, ACT_TANH = 1 };
+
+struct ConvParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  int32_t taps[48];       // per (class, tap): (map << 24) | ((dd+8) << 16) | ((dh+8) << 8) | (dw+8)
+  long long cls_off[4];   // output element offset of each class
+  long long sN, sD, sH, sW, sC;  // output strides (elements)
+  void* out;
+  const float* bias;      // [n_tiles*BN]
+  float* stats;           // [batch][groups][2] (sum, sumsq) or nullptr
+  int bw, bh, bd, rows_valid;
+  int tiles_w, tiles_h, tiles_d, batch;
+  int n_tiles, nclass, ntaps;
+  int src_chunks0, src_chunks1;
+  int W, H, D;            // logical grid of output positions per sample and class
+  int groups, cpg, cout_valid, out_mode, act;
+};
+
+}  // namespace b2v

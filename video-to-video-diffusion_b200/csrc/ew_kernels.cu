@@ -5,6 +5,7 @@
 #include "ew_kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b2v {
 
@@ -49,10 +50,11 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
 // stats_in : [B][G][2] raw (sum, sumsq) over S*cpg elements, produced by the conv epilogue.
 // Grid: (blocks, B); block = C8*R threads, each thread owns 8 fixed channels and strides over rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __restrict__ stats_in,
+template <int U, int MODE, bool STATS>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half* out_, const float* __restrict__ stats_in,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ temb, int temb_stride, const __half* res_, long long S,
-                                int C, int G, float eps, int mode, float* stats_out, int G_out) {
+                                int C, int G, float eps, float* stats_out, int G_out) {
   extern __shared__ float sm[];  // [2*C] when stats_out
   const int C8 = C >> 3;
   const int R = blockDim.x / C8;
@@ -76,7 +78,7 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
     const float ga = gamma[c];
     sc[j] = ga * rstd;
     sh[j] = beta[c] - mean * ga * rstd;
-    ta[j] = (mode == 0 && temb) ? temb[(size_t)b * temb_stride + c] : 0.f;
+    ta[j] = (MODE == 0 && temb) ? temb[(size_t)b * temb_stride + c] : 0.f;
   }
   float as[8], ass[8];
 #pragma unroll
@@ -89,7 +91,6 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
 
   // 4 rows per iteration: all loads are issued before the first use so each thread keeps 4-8 16-byte requests
   // in flight (the kernel is HBM-bound; one request per thread leaves the memory system latency-limited)
-  constexpr int U = 4;
   const long long stride = (long long)gridDim.x * R;
   for (long long row0 = (long long)blockIdx.x * R + rr; row0 < S; row0 += U * stride) {
     uint4 yv[U], rv[U];
@@ -99,7 +100,7 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
       if (row < S) {
         const size_t idx = (size_t)row * C8 + cv;
         yv[k] = y[idx];
-        if (mode == 1 && res) rv[k] = res[idx];
+        if (MODE == 1 && res) rv[k] = res[idx];
       }
     }
 #pragma unroll
@@ -109,7 +110,7 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
       const size_t idx = (size_t)row * C8 + cv;
       float f[8];
       h8_to_f(yv[k], f);
-      if (mode == 0) {
+      if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j]) + ta[j];
       } else {
@@ -125,7 +126,7 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
       }
       const uint4 o = f_to_h8(f);
       out[idx] = o;
-      if (stats_out) {
+      if (STATS) {
         float g[8];
         h8_to_f(o, g);  // statistics of the values the consumer will actually read
 #pragma unroll
@@ -136,7 +137,7 @@ __global__ void gn_apply_kernel(const __half* y_, __half* out_, const float* __r
       }
     }
   }
-  if (stats_out) {
+  if (STATS) {
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
 #pragma unroll
@@ -164,13 +165,30 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
   const int threads = C8 * R;
-  long long want = (S + 4 * R - 1) / (4 * R);
+  static const int U = getenv("B2V_GN_UNROLL") ? atoi(getenv("B2V_GN_UNROLL")) : 4;
+  long long want = (S + U * R - 1) / (U * R);
   long long cap = (148LL * 8 + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
   const size_t smem = stats_out ? 2 * C * sizeof(float) : 0;
-  gn_apply_kernel<<<dim3(blocks, B), threads, smem, st>>>(y, out, stats_in, gamma, beta, temb, temb_stride, res, S, C,
-                                                         G, eps, mode, stats_out, G_out);
+#define GN_LAUNCH(UU, MM, SS)                                                                                     \
+  gn_apply_kernel<UU, MM, SS><<<dim3(blocks, B), threads, smem, st>>>(y, out, stats_in, gamma, beta, temb, temb_stride, \
+                                                                      res, S, C, G, eps, stats_out, G_out)
+#define GN_DISPATCH(UU)                       \
+  do {                                        \
+    if (mode == 0) {                          \
+      if (stats_out) GN_LAUNCH(UU, 0, true);  \
+      else GN_LAUNCH(UU, 0, false);           \
+    } else {                                  \
+      if (stats_out) GN_LAUNCH(UU, 1, true);  \
+      else GN_LAUNCH(UU, 1, false);           \
+    }                                         \
+  } while (0)
+  if (U == 8) GN_DISPATCH(8);
+  else if (U == 2) GN_DISPATCH(2);
+  else GN_DISPATCH(4);
+#undef GN_DISPATCH
+#undef GN_LAUNCH
 }
 
 // Stand-alone statistics pass (used when the producer is not one of our conv / apply kernels, and by tests).
