@@ -167,6 +167,18 @@ def profile_ops(model, dev):
     return out
 
 
+def ncu_traffic():
+    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/, one representative launch; null if no capture has been committed)"""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
+            "algorithmic_bytes_per_launch": sum(d["algorithmic_bytes"].values()), "launch": d["source"]}
+
+
 def roofline_from_profile(prof, pk):
     convs = [o for part in prof.values() for o in part if o["flops"] > 0]
     t_conv = sum(o["ms"] for o in convs) / 1e3
@@ -186,7 +198,7 @@ def roofline_from_profile(prof, pk):
             "share_of_step": round(sum(o["ms"] for o in convs) / max(1e-9, sum(t_all.values())), 4),
             "slowest_launch": {"name": top["name"], "ms": round(top["ms"], 4),
                                "tflops": round(top["flops"] / top["ms"] / 1e9, 1)},
-            "traffic": None,
+            "traffic": ncu_traffic(),
             "hbm_kernels": {"achieved_gbs": round(b_ew / t_ew / 1e9, 1) if t_ew > 0 else None,
                             "peak_gbs": pk["hbm_gbs"], "frac": round(b_ew / t_ew / 1e9 / pk["hbm_gbs"], 4) if t_ew > 0 else None,
                             "note": "GroupNorm-apply / pack / attention-sum kernels, algorithmic bytes / event time"},
