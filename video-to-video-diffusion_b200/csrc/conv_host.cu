@@ -340,14 +340,14 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
 
 void conv_launch(const ConvPlan& P, cudaStream_t st) {
   if (P.swapped) {
-    conv_igemm_t_kernel<<<P.grid, 192, ConvCfgT::SMEM, st>>>(P.p);
+    launch_k(conv_igemm_t_kernel, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
     return;
   }
   switch (P.bn) {
-    case 16: conv_igemm_kernel<16><<<P.grid, 192, ConvCfg<16>::SMEM, st>>>(P.p); break;
-    case 64: conv_igemm_kernel<64><<<P.grid, 192, ConvCfg<64>::SMEM, st>>>(P.p); break;
-    case 128: conv_igemm_kernel<128><<<P.grid, 192, ConvCfg<128>::SMEM, st>>>(P.p); break;
-    default: conv_igemm_kernel<256><<<P.grid, 192, ConvCfg<256>::SMEM, st>>>(P.p); break;
+    case 16: launch_k(conv_igemm_kernel<16>, dim3(P.grid), dim3(192), ConvCfg<16>::SMEM, st, P.p); break;
+    case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(192), ConvCfg<64>::SMEM, st, P.p); break;
+    case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
+    default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
   }
 }
 

@@ -28,7 +28,10 @@ struct ConvCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // narrow heads (BN = 16): back-to-back MMAs into ONE accumulator are latency-bound (each waits for the previous
+  // one), so consecutive k-steps rotate over NSUB independent accumulators that the epilogue adds up
+  static constexpr int NSUB = (BN == 16) ? 4 : 1;
+  static constexpr int TM_COLS = (2 * BN * NSUB < 32) ? 32 : 2 * BN * NSUB;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*group stats*/;
 };
 
@@ -118,6 +121,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptors): let the next kernel start its own, then wait for our producer
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -172,16 +178,18 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN * Cfg::NSUB);
         for (int k = 0; k < ksteps; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+          const uint32_t tmem_d = tmem_acc + (uint32_t)((k % Cfg::NSUB) * BN);
+          const bool first = (k < Cfg::NSUB);  // first k-step landing in this sub-accumulator
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (!first || kk) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == NSTAGE) {
             stage = 0;
@@ -240,15 +248,25 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN * Cfg::NSUB);
+      const int nsub_used = (p.ntaps * chunks < Cfg::NSUB) ? p.ntaps * chunks : Cfg::NSUB;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         float v[CH];
-        if constexpr (CH == 32)
+        if constexpr (CH == 32) {
           tmem_ld_32x32(taddr + c0, v);
-        else
+          tmem_ld_wait();
+        } else {
           tmem_ld_32x16(taddr + c0, v);
-        tmem_ld_wait();
+          tmem_ld_wait();
+          for (int sub = 1; sub < nsub_used; ++sub) {
+            float u[CH];
+            tmem_ld_32x16(taddr + sub * BN + c0, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] += u[j];
+          }
+        }
         const int cg = n0 + c0;
         if (cg >= p.cout_valid) break;
 #pragma unroll

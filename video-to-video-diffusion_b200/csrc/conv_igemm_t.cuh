@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM, descriptors): let the next kernel start its own, then wait for our producer
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {

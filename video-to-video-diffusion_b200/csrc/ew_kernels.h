@@ -22,6 +22,7 @@ struct Coef8 {
 void launch_ddpm_update(float* z, const float* eps, const float* noise, const Coef8& coef, long long n,
                         cudaStream_t st);
 void launch_advance_step(int* step, cudaStream_t st);
+void launch_zero(float* p, long long n, cudaStream_t st);
 void launch_set_t(long long* t_dev, const long long* t_table, const int* step, long long imm, int B, cudaStream_t st);
 void launch_pack_unet_in(const float* z, const float* c, __half* out, int B, int L, int D, int H, int W,
                          cudaStream_t st);

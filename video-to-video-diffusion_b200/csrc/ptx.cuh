@@ -157,6 +157,30 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library calls pdl_trigger() (lets the NEXT kernel in the stream start its prologue on SMs
+// that free up) and then pdl_wait() (blocks until the PREVIOUS kernel has completed and flushed) before it touches
+// memory another kernel may write.  Both are no-ops for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // true when B2V_PDL is set (off by default, see ew_kernels.cu)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -261,7 +261,7 @@ static int build_unet_program(UNet& u, UProgram& up) {
     Op op;
     op.name = "zero_stats";
     op.bytes = (double)bytes;
-    op.run = [=](cudaStream_t st) { cudaMemsetAsync(stats, 0, bytes, st); };
+    op.run = [=](cudaStream_t st) { launch_zero(stats, (long long)(bytes / sizeof(float)), st); };
     b.ops.push_back(std::move(op));
   }
   {

@@ -136,7 +136,7 @@ static int build_vae_program(VAE& v, VProgram& vp, int which) {
     const size_t bytes = vp.stats_cap * sizeof(float);
     Op op;
     op.name = "zero_stats";
-    op.run = [=](cudaStream_t st) { cudaMemsetAsync(stats, 0, bytes, st); };
+    op.run = [=](cudaStream_t st) { launch_zero(stats, (long long)(bytes / sizeof(float)), st); };
     b.ops.push_back(std::move(op));
   }
   if (which == 0) {
