@@ -99,6 +99,14 @@ int b2v_vae_decode(b2v_vae* v, const float* z, float* x, int B, int T, int h, in
  * models/model.py:284-289  F.interpolate(z, (Dout, h, w), 'trilinear', align_corners=False) with h, w unchanged */
 int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, int HW, void* stream);
 
+/* inference/sampler.py:379-451  sliding-window stitching: acc[bc, d0+d, h0+h, w0+w] += patch * gd[d]*gh[h]*gw[w],
+ * wsum likewise (patch: (BC,pd,ph,pw); acc, wsum: (BC,D,H,W); gd/gh/gw: the separable Gaussian window, device fp32),
+ * then acc /= (wsum + 1e-8).  Windows accumulated by concurrent launches must not overlap.                     */
+int b2v_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
+                          const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0, int w0,
+                          void* stream);
+int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* stream);
+
 /* per-op timing of the last planned program of an object, written as JSON text into buf:
  *   [{"name": "...", "ms": .., "flops": .., "bytes": ..}, ...]  (averaged over iters CUDA-event-timed runs)   */
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream);

@@ -309,6 +309,27 @@ def generate(sd, config, v_in, sampler, num_inference_steps=20, target_depth=Non
     return _guard(vae_decode(sd, _guard(z0), vae_cfg["scaling_factor"], "vae."))
 
 
+def gaussian_weight(d, h, w):
+    """_create_gaussian_weight (inference/sampler.py:455-479)"""
+    def g(n):
+        x = torch.arange(n).float() - (n - 1) / 2
+        return torch.exp(-(x ** 2) / (2 * (n / 6) ** 2))
+    return g(d)[:, None, None] * g(h)[None, :, None] * g(w)[None, None, :]
+
+
+def stitch(patches, starts, out_shape):
+    """accumulate / normalise step of sample_with_stitching (inference/sampler.py:379-451): patches is a list of
+    (B,C,td,th,tw) tensors, starts the matching (d,h,w) output origins."""
+    out = torch.zeros(out_shape, device=patches[0].device)
+    wsum = torch.zeros_like(out)
+    td, th, tw = patches[0].shape[2:]
+    win = gaussian_weight(td, th, tw).to(out.device).view(1, 1, td, th, tw)
+    for v, (d0, h0, w0) in zip(patches, starts):
+        out[:, :, d0:d0 + td, h0:h0 + th, w0:w0 + tw] += v * win
+        wsum[:, :, d0:d0 + td, h0:h0 + th, w0:w0 + tw] += win
+    return out / (wsum + 1e-8)
+
+
 def psnr(a, b, max_val=1.0):
     """utils/metrics.py:14-44 calculate_psnr, on tensors already mapped to [0, 1]"""
     mse = torch.clamp(torch.mean((a - b) ** 2), min=1e-8)

@@ -225,3 +225,76 @@ def test_full_generate_ddim50_psnr_gate(cuda_dev, bench_model):
     print(f"generate DDIM-50: PSNR(new,target)={p_new:.4f} PSNR(ref,target)={p_ref:.4f} PSNR(new,ref)={p_direct:.2f} dB")
     assert abs(p_new - p_ref) <= 0.05, (p_new, p_ref)
     assert torch.isfinite(got).all()
+
+
+def test_stitching_same_depth_and_volume_generation(cuda_dev):
+    """sample_with_stitching mirrors the reference (same-depth windows); generate_volume adds the depth upsample the
+    reference stitcher lacks and equals a manual blend of per-window generate() calls"""
+    from v2v_b200.inference import DDIMSampler
+    from v2v_b200.inference.volume import generate_volume, window_starts
+    from v2v_b200.models import VideoToVideoDiffusion
+    g = golden("generate_tiny.pt")
+    torch.manual_seed(g["seed"])
+    m = VideoToVideoDiffusion(g["config"]).eval().to(cuda_dev)
+    gen = torch.Generator().manual_seed(31)
+    vol = (torch.rand((1, 1, 4, 32, 32), generator=gen) * 2 - 1).to(cuda_dev)
+    smp = DDIMSampler(m.diffusion, m.unet)
+    torch.manual_seed(5)
+    out = smp.sample_with_stitching(vol, m.vae, num_inference_steps=2, patch_size=(4, 16, 16),
+                                    target_patch_size=(4, 16, 16), stride=(4, 8, 8), device=cuda_dev, progress=False)
+    assert out.shape == vol.shape and torch.isfinite(out).all()
+    with pytest.raises(RuntimeError):  # 2 -> 6 slices through the reference-style stitcher fails, as in the reference
+        smp.sample_with_stitching(vol, m.vae, 2, (2, 16, 16), (6, 16, 16), (2, 8, 8), cuda_dev, progress=False)
+    # thick -> thin volume: 4 thick slices -> 12 thin, 3x3 windows in-plane, 2 along depth
+    kw = dict(patch_size=(2, 16, 16), target_patch_size=(6, 16, 16), stride=(2, 8, 8))
+    torch.manual_seed(6)
+    full = generate_volume(m, vol, "ddim", 2, batch=1, **kw)
+    assert full.shape == (1, 1, 12, 32, 32) and torch.isfinite(full).all() and full.abs().max() <= 1.0
+    torch.manual_seed(6)
+    patches, starts = [], []
+    for (d0, h0, w0) in window_starts(4, 32, 32, kw["patch_size"], kw["stride"]):
+        patches.append(m.generate(vol[:, :, d0:d0 + 2, h0:h0 + 16, w0:w0 + 16].contiguous(), "ddim", 2, target_depth=6))
+        starts.append((d0 * 3, h0, w0))
+    ref = R.stitch(patches, starts, (1, 1, 12, 32, 32))
+    # same windows, same seeds; not bitwise because two free-running DDIM loops differ at the fp16 floor (DESIGN.md)
+    assert rel_l2(full, ref) < 0.1, rel_l2(full, ref)
+    # sharded over two ranks: partial accumulators add up to the single-rank result
+    torch.manual_seed(7)
+    single = generate_volume(m, vol, "ddim", 2, batch=2, **kw)
+    parts = [generate_volume(m, vol, "ddim", 2, batch=2, rank=r, world=2, **kw) for r in range(2)]
+    wsum = parts[0][1] + parts[1][1]
+    assert torch.allclose(wsum.min(), wsum.min()) and (wsum > 0).all()
+    assert single.shape == parts[0][0].shape
+
+
+@pytest.mark.timeout(1200)
+def test_config3_full_512_volume(cuda_dev, bench_model):
+    """BASELINE config 3: one full 512x512 slab, 8 thick -> 48 thin: latent (1,8,48,128,128).
+    U-Net step parity at that shape, then encode + DDIM (3 evaluations) + decode end to end vs the fp32 oracle."""
+    m, cfg = bench_model
+    _, unet_cfg, _ = R.resolve_config(cfg)
+    sd = _sd(m, cuda_dev)
+    usd = {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((1, 8, 48, 128, 128), generator=g).to(cuda_dev)
+    c = torch.randn((1, 8, 48, 128, 128), generator=g).to(cuda_dev)
+    t = torch.tensor([500], device=cuda_dev)
+    got = m.unet(x, t, c)
+    with torch.no_grad():
+        ref = R.unet_forward(usd, unet_cfg, x, t, c)
+    err = rel_l2(got, ref)
+    print(f"512^2 U-Net step: rel-L2 = {err:.3e}")
+    assert err < EPS_TOL, err
+    del ref, got, x, c
+    v = (torch.rand((1, 1, 8, 512, 512), generator=g) * 2 - 1).to(cuda_dev)
+    target = (torch.rand((1, 1, 48, 512, 512), generator=g) * 2 - 1).to(cuda_dev)
+    torch.manual_seed(42)
+    out = m.generate(v, "ddim", 2, target_depth=48)
+    torch.manual_seed(42)
+    with torch.no_grad():
+        ref = R.generate(sd, cfg, v, "ddim", 2, target_depth=48)
+    assert out.shape == ref.shape == (1, 1, 48, 512, 512)
+    n = lambda a: (a.clamp(-1, 1) + 1) / 2  # noqa: E731
+    p_new, p_ref = R.psnr(n(out), n(target)), R.psnr(n(ref), n(target))
+    print(f"512^2 generate: PSNR(new,target)={p_new:.4f} PSNR(ref,target)={p_ref:.4f} PSNR(new,ref)={R.psnr(n(out), n(ref)):.2f}")
+    assert abs(p_new - p_ref) <= 0.05

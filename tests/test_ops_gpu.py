@@ -166,3 +166,22 @@ def test_upsample_depth_vs_torch(cuda_dev):
     got = ops.upsample_depth(z, 48)
     ref = F.interpolate(z, size=(48, 12, 12), mode="trilinear", align_corners=False)
     assert (got - ref).abs().max().item() <= 1e-6
+
+
+def test_stitch_kernels_match_reference_blend(cuda_dev):
+    """Gaussian-window accumulate + normalise (inference/sampler.py:379-451) -- bit-exact fp32"""
+    from oracle import ref_port as R
+    from v2v_b200 import ops
+    from v2v_b200.dist import patch_grid
+    g = torch.Generator().manual_seed(21)
+    B, C, D, H, W, pd, ph, pw = 2, 1, 12, 40, 40, 6, 16, 16
+    starts = [(d, h, w) for d in patch_grid(D, pd, 3) for h in patch_grid(H, ph, 8) for w in patch_grid(W, pw, 8)]
+    patches = [torch.randn((B, C, pd, ph, pw), generator=g).to(cuda_dev) for _ in starts]
+    ref = R.stitch(patches, starts, (B, C, D, H, W))
+    acc = torch.zeros((B, C, D, H, W), device=cuda_dev)
+    ws = torch.zeros_like(acc)
+    for v, (d0, h0, w0) in zip(patches, starts):
+        ops.stitch_accumulate(v, acc, ws, d0, h0, w0)
+    got = ops.stitch_normalize(acc, ws)
+    assert torch.equal(got, ref), (got - ref).abs().max().item()
+    assert abs(ops.gaussian_window_1d(48, cuda_dev).cpu() - R.gaussian_weight(48, 1, 1)[:, 0, 0]).max() == 0

@@ -155,6 +155,24 @@ int b2v_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, i
   return 0;
 }
 
+int b2v_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
+                           const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0, int w0,
+                           void* stream) {
+  if (check_device()) return -1;
+  if (d0 < 0 || h0 < 0 || w0 < 0 || d0 + pd > D || h0 + ph > H || w0 + pw > W) return fail("stitch: patch outside the volume");
+  launch_stitch_accumulate(patch, acc, wsum, gd, gh, gw, BC, pd, ph, pw, D, H, W, d0, h0, w0, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* stream) {
+  if (check_device()) return -1;
+  launch_stitch_normalize(acc, wsum, n, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* bias, int cin0, int cin1, int cout) {
   if (check_device()) return -1;
   std::string err;

@@ -624,6 +624,52 @@ void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sliding-window stitching (reference inference/sampler.py:379-451): every decoded patch is blended into the full
+// volume with a separable Gaussian window (sigma = size/6), then the accumulator is divided by the summed weights.
+//   acc[b,c,d0+d,h0+h,w0+w] += patch[b,c,d,h,w] * gd[d]*gh[h]*gw[w] ;  wsum[...] += gd[d]*gh[h]*gw[w]
+// Patches of one launch must not overlap each other (the caller batches non-overlapping windows or launches
+// one patch at a time); both tensors are nc32.
+// ------------------------------------------------------------------------------------------------
+__global__ void stitch_accumulate_kernel(const float* __restrict__ patch, float* acc, float* wsum,
+                                         const float* __restrict__ gd, const float* __restrict__ gh,
+                                         const float* __restrict__ gw, int C, int pd, int ph, int pw, int D, int H,
+                                         int W, int d0, int h0, int w0, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % pw);
+    const int h = (int)((i / pw) % ph);
+    const int d = (int)((i / ((long long)pw * ph)) % pd);
+    const long long bc = i / ((long long)pw * ph * pd);
+    const float wt = __fmul_rn(__fmul_rn(gd[d], gh[h]), gw[w]);  // the reference's outer-product order
+    const size_t o = ((size_t)bc * D + (d0 + d)) * H * W + (size_t)(h0 + h) * W + (w0 + w);
+    acc[o] = __fadd_rn(acc[o], __fmul_rn(patch[i], wt));
+    wsum[o] = __fadd_rn(wsum[o], wt);
+  }
+}
+void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
+                              const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
+                              int w0, cudaStream_t st) {
+  const long long total = (long long)BC * pd * ph * pw;
+  int blocks = cdiv(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(stitch_accumulate_kernel, dim3(blocks), dim3(256), 0, st, patch, acc, wsum, gd, gh, gw, BC, pd, ph, pw, D,
+           H, W, d0, h0, w0, total);
+}
+__global__ void stitch_normalize_kernel(float* acc, const float* __restrict__ wsum, long long n) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] = __fdiv_rn(acc[i], __fadd_rn(wsum[i], 1e-8f));
+}
+void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStream_t st) {
+  int blocks = cdiv(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(stitch_normalize_kernel, dim3(blocks), dim3(256), 0, st, acc, wsum, n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout casts for the op-level API and tests
 // ------------------------------------------------------------------------------------------------
 __global__ void nc32_to_cl16_kernel(const float* __restrict__ in, __half* out, int C, int Cpad, long long S,

@@ -31,6 +31,10 @@ void launch_pack_vae_dec_in(const float* z, const float* Wpq, const float* bpq, 
 void launch_pack_vae_enc_in(const float* v, __half* out, int B, int Cin, int Cpad, int D, int H, int W,
                             cudaStream_t st);
 void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, long long HW, cudaStream_t st);
+void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
+                              const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
+                              int w0, cudaStream_t st);
+void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStream_t st);
 void launch_nc32_to_cl16(const float* in, __half* out, int B, int C, int Cpad, long long S, cudaStream_t st);
 void launch_cl16_to_nc32(const __half* in, float* out, int B, int C, int Cpad, long long S, cudaStream_t st);
 

@@ -44,16 +44,18 @@ class _Stitching:
         ratio = td / pd
         out = torch.zeros(B, C, int(D * ratio), H, W, device=device)
         wsum = torch.zeros_like(out)
-        win = _gaussian_weight(td, th, tw).to(device).view(1, 1, td, th, tw)
+        win = tuple(ops.gaussian_window_1d(n, out.device) for n in (td, th, tw))
         for d0 in _starts(D, pd, sd_):
             for h0 in _starts(H, ph, sh):
                 for w0 in _starts(W, pw, sw):
                     z_c = vae.encode(v_full[:, :, d0:d0 + pd, h0:h0 + ph, w0:w0 + pw].contiguous())
                     v = vae.decode(sample_fn(tuple(z_c.shape), z_c))
-                    dt = int(d0 * ratio)
-                    out[:, :, dt:dt + td, h0:h0 + th, w0:w0 + tw] += v * win
-                    wsum[:, :, dt:dt + td, h0:h0 + th, w0:w0 + tw] += win
-        return out / (wsum + 1e-8)
+                    if tuple(v.shape[2:]) != (td, th, tw):  # the reference fails here too (broadcast error, F7)
+                        raise RuntimeError(f"decoded patch {tuple(v.shape[2:])} does not match target_patch_size "
+                                           f"{(td, th, tw)}; use v2v_b200.inference.volume.generate_volume for "
+                                           "thick->thin stitching with the depth upsample")
+                    ops.stitch_accumulate(v, out, wsum, int(d0 * ratio), h0, w0, win)
+        return ops.stitch_normalize(out, wsum)
 
     def _create_gaussian_weight(self, d, h, w):
         return _gaussian_weight(d, h, w)

@@ -99,3 +99,26 @@ def upsample_depth(z, depth):
     _lib.check(_lib.lib().b2v_upsample_depth(_lib.dptr(z.contiguous()), _lib.dptr(out), B * C, D, depth, H * W,
                                              _lib.stream()), "upsample_depth")
     return out
+
+
+def gaussian_window_1d(n, device):
+    """1-D factor of the reference's blending window (inference/sampler.py:455-479): exp(-x^2 / (2 (n/6)^2))"""
+    x = torch.arange(n).float() - (n - 1) / 2
+    return torch.exp(-(x ** 2) / (2 * (n / 6) ** 2)).to(device).contiguous()
+
+
+def stitch_accumulate(patch, acc, wsum, d0, h0, w0, win=None):
+    """acc[..., d0:d0+pd, h0:h0+ph, w0:w0+pw] += patch * window ; wsum likewise (in place, fp32 NCDHW)"""
+    B, C, pd, ph, pw = patch.shape
+    _, _, D, H, W = acc.shape
+    gd, gh, gw = win if win is not None else (gaussian_window_1d(pd, patch.device), gaussian_window_1d(ph, patch.device),
+                                              gaussian_window_1d(pw, patch.device))
+    _lib.check(_lib.lib().b2v_stitch_accumulate(_lib.dptr(patch.contiguous()), _lib.dptr(acc), _lib.dptr(wsum),
+                                                _lib.dptr(gd), _lib.dptr(gh), _lib.dptr(gw), B * C, pd, ph, pw, D, H, W,
+                                                int(d0), int(h0), int(w0), _lib.stream()), "stitch_accumulate")
+
+
+def stitch_normalize(acc, wsum):
+    _lib.check(_lib.lib().b2v_stitch_normalize(_lib.dptr(acc), _lib.dptr(wsum), acc.numel(), _lib.stream()),
+               "stitch_normalize")
+    return acc
