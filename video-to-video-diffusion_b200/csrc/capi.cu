@@ -14,6 +14,8 @@ struct b2v_vae {
 };
 struct b2v_conv {
   ConvLayer L;
+  float* ws = nullptr;  // tap-GEMM workspace of narrow heads (grown on demand)
+  size_t ws_bytes = 0;
 };
 
 static int check_device() {
@@ -186,18 +188,30 @@ int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* 
   return 0;
 }
 void b2v_conv_destroy(b2v_conv* c) {
-  if (c) conv_layer_free(c->L);
+  if (c) {
+    conv_layer_free(c->L);
+    if (c->ws) cudaFree(c->ws);
+  }
   delete c;
 }
 int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, float* stats, int groups,
                      int act_tanh, int N, int D, int H, int W, void* stream) {
   ConvPlan P;
   std::string err;
+  const size_t need_ws = (out_fp32 && !in1 && !stats) ? conv_tap_ws_bytes(c->L, N, D, H, W) : 0;
+  if (need_ws > c->ws_bytes) {
+    B2V_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (c->ws) cudaFree(c->ws);
+    c->ws = nullptr;
+    c->ws_bytes = 0;
+    B2V_CUDA(cudaMalloc(&c->ws, need_ws));
+    c->ws_bytes = need_ws;
+  }
   if (conv_plan(P, c->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, out_fp32 ? OUT_F32 : OUT_CL16, stats,
-                groups, act_tanh ? ACT_TANH : ACT_NONE, err))
+                groups, act_tanh ? ACT_TANH : ACT_NONE, err, need_ws ? c->ws : nullptr))
     return fail(err);
   conv_launch(P, (cudaStream_t)stream);
-  g_launches += 1;
+  g_launches += P.tapgemm ? 2 : 1;
   B2V_CUDA(cudaGetLastError());
   return 0;
 }

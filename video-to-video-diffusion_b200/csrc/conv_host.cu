@@ -1,6 +1,7 @@
 #include "conv_host.h"
 
 #include "conv_igemm_t.cuh"
+#include "ew_kernels.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -69,7 +70,9 @@ int conv_setup_kernels(std::string& err) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<256>::SMEM);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_igemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
+    e = cudaFuncSetAttribute(conv_igemm_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
   if (e != cudaSuccess) {
     err = std::string("cudaFuncSetAttribute(conv_igemm): ") + cudaGetErrorString(e);
     return -1;
@@ -199,12 +202,41 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)L.cout_pad, (cuuint64_t)nt};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * L.cout_pad * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)L.bn, 1};
-  return encode_map(&L.tmB, L.w, 3, dims, strides, box, err);
+  if (encode_map(&L.tmB, L.w, 3, dims, strides, box, err)) return -1;
+  if (kind == CONV_K3 && cout <= 16 && cin1 == 0) {
+    // tap-GEMM layout: row (tap*Cout + co) holds w[co][:, tap]
+    L.tap_row_tiles = (27 * cout + 127) / 128;
+    const int rows = L.tap_row_tiles * 128;
+    std::vector<__half> wg((size_t)rows * cin, __float2half(0.f));
+    for (int t = 0; t < 27; ++t)
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+        {
+          // logical row r = t*cout + co lives in UMMA row (r % 4) * 32 + r / 4 of its 128-row tile (see MODE 1 epilogue)
+          const int r = t * cout + co, tile = r / 128, rl = r % 128;
+          const int phys = tile * 128 + (rl % 4) * 32 + rl / 4;
+          wg[(size_t)phys * cin + ci] = __float2half_rn(wc(co, ci, t / 9, (t / 3) % 3, t % 3));
+        }
+    e = cudaMalloc(&L.wg, wg.size() * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMemcpy(L.wg, wg.data(), wg.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      err = std::string("conv tap-gemm weights upload: ") + cudaGetErrorString(e);
+      return -1;
+    }
+    cuuint64_t gd[3] = {(cuuint64_t)cin, (cuuint64_t)rows, 1};
+    cuuint64_t gs[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * rows * 2};
+    cuuint32_t gb[3] = {64, 128, 1};
+    if (encode_map(&L.tmBg, L.wg, 3, gd, gs, gb, err)) return -1;
+    L.tapgemm = true;
+  }
+  return 0;
 }
 
 void conv_layer_free(ConvLayer& L) {
   if (L.w) cudaFree(L.w);
   if (L.bias) cudaFree(L.bias);
+  if (L.wg) cudaFree(L.wg);
+  L.wg = nullptr;
   L.w = nullptr;
   L.bias = nullptr;
 }
@@ -228,11 +260,69 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
+static inline long long tap_pairs(long long positions) { return ((positions + 127) / 128 + 1) / 2; }
+
+size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
+  static const bool off = getenv("B2V_NO_TAPGEMM") != nullptr;
+  if (!L.tapgemm || off) return 0;
+  return (size_t)27 * L.cout * (size_t)(tap_pairs((long long)N * D * H * W) * 256) * sizeof(float);
+}
+
+// GEMM over the flattened volume: P[(tap,co)][position] = sum_c w[co][c][tap] * x[position][c]
+static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int N, int D, int H, int W, void* out,
+                        int act, std::string& err, float* ws) {
+  ConvParams& p = P.p;
+  const long long pos = (long long)N * D * H * W;
+  const long long pairs = tap_pairs(pos);
+  p.bw = 128;
+  p.bh = p.bd = 1;
+  p.rows_valid = 128;
+  p.tiles_w = (int)((pos + 127) / 128);
+  p.tiles_h = p.tiles_d = 1;
+  p.batch = 1;
+  p.n_tiles = L.tap_row_tiles;
+  p.nclass = 1;
+  p.ntaps = 1;
+  p.src_chunks0 = L.cin0_pad / 64;
+  p.src_chunks1 = 0;
+  p.taps[0] = enc_tap(0, 0, 0, 0);
+  p.tmB = L.tmBg;
+  p.W = (int)pos;
+  p.H = p.D = 1;
+  p.cpg = 1;
+  p.cout_valid = 27 * L.cout;
+  p.out = ws;
+  p.sC = pairs * 256;
+  const cuuint64_t C = L.cin0_pad;
+  cuuint64_t dims[5] = {C, (cuuint64_t)pos, 1, 1, 1};
+  cuuint64_t st[4] = {C * 2, (cuuint64_t)pos * C * 2, (cuuint64_t)pos * C * 2, (cuuint64_t)pos * C * 2};
+  cuuint32_t box[5] = {64, 128, 1, 1, 1};
+  if (encode_map(&p.tmA[0], in0, 5, dims, st, box, err)) return -1;
+  P.tapgemm = true;
+  P.st.P = ws;
+  P.st.bias = L.bias;
+  P.st.out = (float*)out;
+  P.st.N = N;
+  P.st.cout = L.cout;
+  P.st.D = D;
+  P.st.H = H;
+  P.st.W = W;
+  P.st.act = act;
+  P.st.row_stride = pairs * 256;
+  const long long total = pairs * L.tap_row_tiles;
+  const int sms = device_sm_count();
+  P.grid = (int)(total < sms ? total : sms);
+  P.flops = 2.0 * (double)pos * 27.0 * (double)L.cin0 * (double)L.cout;
+  return 0;
+}
+
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err) {
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws) {
   memset(&P, 0, sizeof(P));
   ConvParams& p = P.p;
   P.bn = L.bn;
+  if (tap_ws && out_mode == OUT_F32 && !in1 && !stats && conv_tap_ws_bytes(L, N, D, H, W))
+    return plan_tapgemm(P, L, in0, N, D, H, W, out, act, err, tap_ws);
   if ((L.cin1 != 0) != (in1 != nullptr)) {
     err = "conv_plan: second source mismatch";
     return -1;
@@ -339,8 +429,15 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
 }
 
 void conv_launch(const ConvPlan& P, cudaStream_t st) {
+  if (P.tapgemm) {
+    static const int dbg = getenv("B2V_TAP_DEBUG") ? atoi(getenv("B2V_TAP_DEBUG")) : 0;  // 1: GEMM only, 2: stencil only
+    if (dbg != 2) launch_k(conv_igemm_t_kernel<1>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
+    if (dbg != 1) launch_head_stencil(P.st.P, P.st.bias, P.st.out, P.st.N, P.st.cout, P.st.D, P.st.H, P.st.W, P.st.row_stride,
+                        P.st.act, st);
+    return;
+  }
   if (P.swapped) {
-    launch_k(conv_igemm_t_kernel, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
+    launch_k(conv_igemm_t_kernel<0>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
     return;
   }
   switch (P.bn) {

@@ -28,6 +28,11 @@ struct ConvLayer {
   float* bias = nullptr; // device [cout_pad]
   CUtensorMap tmB;
   int32_t taps[48];
+  // narrow 3x3x3 heads (Cout <= 16, Cin % 64 == 0): second weight layout for the tap-GEMM path
+  bool tapgemm = false;
+  int tap_row_tiles = 0;    // ceil(27*Cout / 128)
+  __half* wg = nullptr;     // device [tap_row_tiles*128][Cin]: row = tap*Cout + co
+  CUtensorMap tmBg;
 };
 
 struct ConvPlan {
@@ -35,6 +40,15 @@ struct ConvPlan {
   int bn = 0;
   int grid = 0;
   bool swapped = false;  // Cout == 128: operand-swapped kernel (conv_igemm_t.cuh)
+  // tap-GEMM head: p describes the GEMM, the stencil pass below turns its rows into the NCDHW fp32 output
+  bool tapgemm = false;
+  struct {
+    const float* P;
+    const float* bias;
+    float* out;
+    int N, cout, D, H, W, act;
+    long long row_stride;
+  } st;
   double flops = 0;  // algorithmic 2*MAC of the reference convolution (no padding / packing waste)
 };
 
@@ -46,7 +60,9 @@ void conv_layer_free(ConvLayer& L);
 // in0/in1: NDHWC fp16 [N][D][H][W][cin*_pad]; (D,H,W) are the INPUT dims.
 // out_mode OUT_CL16: out is NDHWC fp16 with cout channels; OUT_F32: out is NCDHW fp32 with cout channels.
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err);
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws = nullptr);
+// bytes of fp32 workspace the tap-GEMM path of a narrow head needs for this input (0: layer has no such path)
+size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W);
 void conv_launch(const ConvPlan& P, cudaStream_t st);
 int conv_setup_kernels(std::string& err);  // opt-in to large dynamic shared memory; call once per device
 int device_sm_count();

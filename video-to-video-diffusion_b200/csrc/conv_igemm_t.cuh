@@ -22,10 +22,15 @@ struct ConvCfgT {
   static constexpr int STAGE = W_BYTES + P_BYTES;
   static constexpr int NSTAGE = 4;
   static constexpr int TM_COLS = 512;
-  static constexpr int XPOSE = 4 * 32 * 32 * 2;  // per-epilogue-warp 32x32 fp16 transpose tile
+  static constexpr int XPOSE = 4 * 32 * 33 * 4;  // per-epilogue-warp transpose tile (32x32 fp16, or 32x33 fp32 in MODE 1)
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + 1024 + XPOSE;
 };
 
+// MODE 0: convolution (above).  MODE 1 ("tap GEMM", narrow heads Cout <= 16): the 128 "channel" rows are
+// (tap, cout) pairs of a 3x3x3 filter, the positions are the flattened volume with no halo, and the raw fp32
+// products P[tap*Cout+co][position] are stored row-wise; head_stencil_kernel then sums the 27 shifted rows.
+// The input is read ONCE instead of once per tap (the N=16 implicit GEMM was L2-bound at ~7 TB/s).
+template <int MODE>
 __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfgT;
   constexpr int NSTAGE = Cfg::NSTAGE;
@@ -42,8 +47,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;  // even per sample (checked on the host)
-  const int pairs = m_tiles >> 1;
-  const int total = pairs * p.nclass;
+  const int pairs = (m_tiles + 1) >> 1;
+  const int total = pairs * (MODE ? p.n_tiles : p.nclass);
   const int chunks = p.src_chunks0 + p.src_chunks1;
 
   if (threadIdx.x == 0) {
@@ -75,7 +80,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int cls = tile / pairs;
+        const int cls = MODE ? 0 : tile / pairs;
+        const int n0 = MODE ? (tile / pairs) * 128 : 0;
         const int pm = tile % pairs;
         int w0[2], h0[2], d0[2], nb[2];
 #pragma unroll
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], 2u * a_bytes + (uint32_t)Cfg::W_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE;
-            tma_load_3d(sa, &p.tmB, &full[stage], c * 64, 0, tg);
+            tma_load_3d(sa, &p.tmB, &full[stage], c * 64, n0, tg);
             tma_load_5d(sa + Cfg::W_BYTES, &p.tmA[map + src], &full[stage], cc * 64, w0[0] + ow, h0[0] + oh,
                         d0[0] + od, nb[0]);
             tma_load_5d(sa + Cfg::W_BYTES + 16384, &p.tmA[map + src], &full[stage], cc * 64, w0[1] + ow, h0[1] + oh,
@@ -149,8 +155,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     const int ch = q * 32 + lane;
     const int et = threadIdx.x - 64;
     const int ng = 128 / p.cpg;
-    const float bias_c = __ldg(p.bias + ch);
-    __half* xp = xpose + (warp - 2) * 1024;  // 32 positions x 32 channels
+    const float bias_c = MODE ? 0.f : __ldg(p.bias + ch);
+    __half* xp = xpose + (warp - 2) * 1024;  // 32 positions x 32 channels (MODE 0)
     __half* outp = reinterpret_cast<__half*>(p.out);
     int cur_nb = -1;
     auto flush = [&]() {
@@ -166,11 +172,40 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int cls = tile / pairs;
+      const int cls = MODE ? 0 : tile / pairs;
       const int pm = tile % pairs;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      if constexpr (MODE == 1) {
+        // raw rows: TMEM lane = (tap, cout) row, columns = positions.  A 32x32 fp32 block is transposed through
+        // shared memory (row pitch 33: conflict-free both ways) so that every store instruction writes one full
+        // 128-byte line of ONE row (16-byte pieces scattered over 27+ rows made DRAM writes crawl once P outgrew L2)
+        // logical row r of a 128-row tile sits in TMEM lane (r % 4) * 32 + r / 4 (weights are packed that way), so
+        // the valid rows of a narrow head (27 for Cout = 1) are spread over all four epilogue warps
+        const int tbase = (tile / pairs) * 128;
+        const int rows_in_tile = min(128, p.cout_valid - tbase);
+        float* xf = reinterpret_cast<float*>(xpose) + (warp - 2) * (32 * 33);
+        float* pbase = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+        for (int ci = 0; ci < 8; ++ci) {
+          float v[32];
+          tmem_ld_32x32(taddr + ci * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xf[lane * 33 + j] = v[j];
+          __syncwarp();
+          const long long pos0 = (long long)(2 * pm + (ci >> 2)) * 128 + (ci & 3) * 32 + lane;
+          const int nrows = (rows_in_tile - q + 3) >> 2;  // this warp owns logical rows q, q+4, q+8, ...
+          for (int rr = 0; rr < nrows; ++rr)
+            pbase[(size_t)(tbase + rr * 4 + q) * (size_t)p.sC + pos0] = xf[rr * 33 + lane];
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        continue;
+      }
 #pragma unroll 1
       for (int ci = 0; ci < 8; ++ci) {
         // this lane's "own" position of the chunk: row r of box (ci >> 2)

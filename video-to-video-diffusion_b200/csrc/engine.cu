@@ -224,8 +224,20 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
   }
   ConvPlan P;
   std::string err;
-  if (conv_plan(P, L, in0.p, in1 ? in1->p : nullptr, B, in0.D, in0.H, in0.W, out_fp32 ? (void*)out_fp32 : (void*)out.p,
-                out_fp32 ? OUT_F32 : OUT_CL16, stats, groups, act, err)) {
+  float* ws = nullptr;
+  const size_t ws_bytes = (out_fp32 && !in1 && !stats) ? conv_tap_ws_bytes(L, B, in0.D, in0.H, in0.W) : 0;
+  if (ws_bytes) {
+    ws = (float*)pool.get(ws_bytes);  // live only during this op: returned to the pool right after planning
+    if (!ws) {
+      ok = false;
+      return out;
+    }
+  }
+  const int rc = conv_plan(P, L, in0.p, in1 ? in1->p : nullptr, B, in0.D, in0.H, in0.W,
+                           out_fp32 ? (void*)out_fp32 : (void*)out.p, out_fp32 ? OUT_F32 : OUT_CL16, stats, groups, act,
+                           err, ws);
+  if (ws) pool.put(ws);
+  if (rc) {
     fail(name + ": " + err);
     ok = false;
     return out;
@@ -235,6 +247,7 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
   op.name = name;
   op.flops = P.flops;
   op.bytes = 0;
+  op.launches = P.tapgemm ? 2 : 1;
   op.out = out_fp32 ? (void*)out_fp32 : (void*)out.p;
   op.out_bytes = out_fp32 ? (size_t)B * L.cout * oD * oH * oW * 4 : (size_t)B * oD * oH * oW * L.cout * 2;
   op.run = [P](cudaStream_t st) { conv_launch(P, st); };

@@ -624,6 +624,39 @@ void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow 3x3x3 heads (Cout <= 16: U-Net conv_out, VAE encoder/decoder conv_out), second half: the tap GEMM wrote
+// P[(tap*Cout+co)][position]; out[n,co,d,h,w] = bias[co] + sum_tap P[tap*Cout+co][pos(n,d+dd,h+dh,w+dw)] over the
+// in-bounds taps (zero padding), optional tanh, fp32 NCDHW.  HBM-bound: every P element is read exactly once.
+// ------------------------------------------------------------------------------------------------
+__global__ void head_stencil_kernel(const float* __restrict__ P, const float* __restrict__ bias, float* out,
+                                    int cout, int D, int H, int W, long long row_stride, int act, long long total) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (n, co, d, h, w)
+  if (i >= total) return;
+  const int w = (int)(i % W);
+  const int h = (int)((i / W) % H);
+  const int d = (int)((i / ((long long)W * H)) % D);
+  const int co = (int)((i / ((long long)W * H * D)) % cout);
+  const long long n = i / ((long long)W * H * D * cout);
+  const long long base = ((n * D + d) * H + h) * W + w;
+  float acc = bias[co];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int dd = t / 9 - 1, dh = (t / 3) % 3 - 1, dw = t % 3 - 1;
+    if ((unsigned)(d + dd) < (unsigned)D && (unsigned)(h + dh) < (unsigned)H && (unsigned)(w + dw) < (unsigned)W)
+      acc += P[(size_t)(t * cout + co) * row_stride + base + ((long long)dd * H + dh) * W + dw];
+  }
+  out[i] = act ? tanhf(acc) : acc;
+}
+void launch_head_stencil(const float* P, const float* bias, float* out, int N, int cout, int D, int H, int W,
+                         long long row_stride, int act, cudaStream_t st) {
+  const long long total = (long long)N * cout * D * H * W;
+  launch_k(head_stencil_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, P, bias, out, cout, D, H, W, row_stride, act,
+           total);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sliding-window stitching (reference inference/sampler.py:379-451): every decoded patch is blended into the full
 // volume with a separable Gaussian window (sigma = size/6), then the accumulator is divided by the summed weights.
 //   acc[b,c,d0+d,h0+h,w0+w] += patch[b,c,d,h,w] * gd[d]*gh[h]*gw[w] ;  wsum[...] += gd[d]*gh[h]*gw[w]

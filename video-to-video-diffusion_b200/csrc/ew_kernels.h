@@ -31,6 +31,8 @@ void launch_pack_vae_dec_in(const float* z, const float* Wpq, const float* bpq, 
 void launch_pack_vae_enc_in(const float* v, __half* out, int B, int Cin, int Cpad, int D, int H, int W,
                             cudaStream_t st);
 void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, long long HW, cudaStream_t st);
+void launch_head_stencil(const float* P, const float* bias, float* out, int N, int cout, int D, int H, int W,
+                         long long row_stride, int act, cudaStream_t st);
 void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
                               const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
                               int w0, cudaStream_t st);
