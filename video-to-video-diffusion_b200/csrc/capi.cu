@@ -89,6 +89,7 @@ int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise,
 int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) { return u->u.sampler_end(z_out, (cudaStream_t)stream); }
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream) {
   if (!u->u.last) return fail("unet_profile: run a forward first");
+  u->u.last->temb = TembSource{u->u.last->proj, u->u.last->desc_rows, nullptr, 0};
   std::string js;
   if (u->u.last->fwd.profile(iters, (cudaStream_t)stream, js)) return -1;
   return write_json(js, buf, cap);
@@ -124,6 +125,7 @@ int b2v_vae_profile(b2v_vae* v, int which, int iters, char* buf, size_t cap, voi
 static Program* debug_prog(void* obj, int prog) {
   if (prog == 0) {
     UNet& u = ((b2v_unet*)obj)->u;
+    if (u.last) u.last->temb = TembSource{u.last->proj, u.last->desc_rows, nullptr, 0};
     return u.last ? &u.last->fwd : nullptr;
   }
   VAE& v = ((b2v_vae*)obj)->v;
@@ -232,7 +234,7 @@ int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* g
                  int G_out, void* stream) {
   if (C % 8 || C / 8 > 256) return fail("gn_apply: C must be a multiple of 8 and <= 2048");
   launch_gn_apply((const __half*)y, (__half*)out, stats_in, gamma, beta, temb, C, (const __half*)res, B, S, C, G, 1e-5f,
-                  mode, stats_out, G_out, (cudaStream_t)stream);
+                  mode, stats_out, G_out, (cudaStream_t)stream, nullptr, 0);
   g_launches += 1;
   B2V_CUDA(cudaGetLastError());
   return 0;

@@ -60,8 +60,29 @@ int device_sm_count() {
   return g_sms;
 }
 
+// B2V_OPERANDS=bf16: operand-precision study (see ptx.cuh); weights are rounded to BF16 precision at pack time
+static bool operands_bf16() {
+  static const bool on = getenv("B2V_OPERANDS") && std::string(getenv("B2V_OPERANDS")) == "bf16";
+  return on;
+}
+static inline __half to_operand(float x) {
+  if (operands_bf16()) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    u &= 0xFFFF0000u;
+    memcpy(&x, &u, 4);
+  }
+  return __float2half_rn(x);
+}
+
 int conv_setup_kernels(std::string& err) {
   cudaError_t e;
+  {
+    const int on = operands_bf16() ? 1 : 0;
+    cudaMemcpyToSymbol(c_round_bf16, &on, sizeof(int));
+    ew_set_round_bf16(on);
+  }
   e = cudaFuncSetAttribute(conv_igemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<16>::SMEM);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::SMEM);
@@ -142,7 +163,7 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
           const int t = (kd * kh_n + kh) * kw_n + kw;
           L.taps[t] = (kind == CONV_K1) ? enc_tap(0, 0, 0, 0) : enc_tap(0, kd - 1, kh - 1, kw - 1);
           for (int co = 0; co < cout; ++co)
-            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = to_operand(wc(co, ci, kd, kh, kw));
         }
   } else if (kind == CONV_DOWN) {
     // input index 2*o + k - 1  ->  parity view p, offset dlt:  k=0:(1,-1) 1:(0,0) 2:(1,0) 3:(0,+1)
@@ -153,7 +174,7 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
           const int t = (kd * 4 + kh) * 4 + kw;
           L.taps[t] = enc_tap(par[kh] * 2 + par[kw], kd - 1, dlt[kh], dlt[kw]);
           for (int co = 0; co < cout; ++co)
-            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+            for (int ci = 0; ci < cin; ++ci) W(t, co, ci) = to_operand(wc(co, ci, kd, kh, kw));
         }
   } else if (kind == CONV_UPT) {
     // out(od, 2j+ph, 2i+pw) = sum in(od+1-kd, j+dh, i+dw) * w[ci][co][kd][kh][kw]
@@ -170,7 +191,7 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
               L.taps[t] = enc_tap(0, 1 - kd, ds[ph][a], ds[pw][c2]);
               for (int co = 0; co < cout; ++co)
                 for (int ci = 0; ci < cin; ++ci)
-                  W(t, co, ci) = __float2half_rn(w[((((size_t)ci * cout + co) * 3 + kd) * 4 + kh) * 4 + kw]);
+                  W(t, co, ci) = to_operand(w[((((size_t)ci * cout + co) * 3 + kd) * 4 + kh) * 4 + kw]);
             }
   } else if (kind == CONV_K3_PACKW) {
     for (int kd = 0; kd < 3; ++kd)
@@ -179,14 +200,14 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
         L.taps[t] = enc_tap(0, kd - 1, kh - 1, 0);
         for (int co = 0; co < cout; ++co)
           for (int kw = 0; kw < 3; ++kw)
-            for (int ci = 0; ci < cin; ++ci) W(t, co, kw * cin + ci) = __float2half_rn(wc(co, ci, kd, kh, kw));
+            for (int ci = 0; ci < cin; ++ci) W(t, co, kw * cin + ci) = to_operand(wc(co, ci, kd, kh, kw));
       }
   } else {  // PACKALL
     L.taps[0] = enc_tap(0, 0, 0, 0);
     for (int co = 0; co < cout; ++co)
       for (int tp = 0; tp < 27; ++tp)
         for (int ci = 0; ci < cin; ++ci)
-          W(0, co, tp * cin + ci) = __float2half_rn(wc(co, ci, tp / 9, (tp / 3) % 3, tp % 3));
+          W(0, co, tp * cin + ci) = to_operand(wc(co, ci, tp / 9, (tp / 3) % 3, tp % 3));
   }
   std::vector<float> bp(L.cout_pad, 0.f);
   if (b)
@@ -215,7 +236,7 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
           // logical row r = t*cout + co lives in UMMA row (r % 4) * 32 + r / 4 of its 128-row tile (see MODE 1 epilogue)
           const int r = t * cout + co, tile = r / 128, rl = r % 128;
           const int phys = tile * 128 + (rl % 4) * 32 + rl / 4;
-          wg[(size_t)phys * cin + ci] = __float2half_rn(wc(co, ci, t / 9, (t / 3) % 3, t % 3));
+          wg[(size_t)phys * cin + ci] = to_operand(wc(co, ci, t / 9, (t / 3) % 3, t % 3));
         }
     e = cudaMalloc(&L.wg, wg.size() * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemcpy(L.wg, wg.data(), wg.size() * sizeof(__half), cudaMemcpyHostToDevice);

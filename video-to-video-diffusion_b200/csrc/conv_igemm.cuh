@@ -290,10 +290,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
             __half* o = reinterpret_cast<__half*>(p.out) + roff + cg;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
-              __half2 h0 = __floats2half2_rn(v[j + 0], v[j + 1]);
-              __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-              __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
-              __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+              __half2 h0 = __floats2half2_rn(operand_round(v[j + 0]), operand_round(v[j + 1]));
+              __half2 h1 = __floats2half2_rn(operand_round(v[j + 2]), operand_round(v[j + 3]));
+              __half2 h2 = __floats2half2_rn(operand_round(v[j + 4]), operand_round(v[j + 5]));
+              __half2 h3 = __floats2half2_rn(operand_round(v[j + 6]), operand_round(v[j + 7]));
               uint4 u;
               u.x = *reinterpret_cast<uint32_t*>(&h0);
               u.y = *reinterpret_cast<uint32_t*>(&h1);

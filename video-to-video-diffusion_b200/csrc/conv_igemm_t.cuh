@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         }
         // 32 channels x 32 positions -> [position][channel] through shared memory, then 16-byte row stores
 #pragma unroll
-        for (int j = 0; j < 32; ++j) xp[j * 32 + lane] = __float2half_rn(v[j]);
+        for (int j = 0; j < 32; ++j) xp[j * 32 + lane] = __float2half_rn(operand_round(v[j]));
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

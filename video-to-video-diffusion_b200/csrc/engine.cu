@@ -255,8 +255,8 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
   return out;
 }
 
-void Builder::gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, const float* temb,
-                       int temb_stride, const Act* res, int mode, float* stats_out, int G_out) {
+void Builder::gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, int temb_off,
+                       const Act* res, int mode, float* stats_out, int G_out) {
   const int Bc = B;
   const long long S = y.S();
   const int C = y.C;
@@ -264,13 +264,16 @@ void Builder::gn_apply(const std::string& name, Act& y, const float* stats_in, c
   const __half* rp = res ? res->p : nullptr;
   const float *ga = g.gamma, *be = g.beta;
   const int G = g.G;
+  const TembSource* ts = (temb_off >= 0) ? temb_src : nullptr;
   Op op;
   op.name = name;
   op.bytes = (double)Bc * S * C * 2.0 * (res ? 3.0 : 2.0);
   op.out = yp;
   op.out_bytes = (size_t)Bc * S * C * 2;
   op.run = [=](cudaStream_t st) {
-    launch_gn_apply(yp, yp, stats_in, ga, be, temb, temb_stride, rp, Bc, S, C, G, 1e-5f, mode, stats_out, G_out, st);
+    const float* tp = ts ? ts->base + temb_off : nullptr;
+    launch_gn_apply(yp, yp, stats_in, ga, be, tp, ts ? ts->sample_stride : 0, rp, Bc, S, C, G, 1e-5f, mode, stats_out,
+                    G_out, st, ts ? ts->step_ptr : nullptr, ts ? ts->step_stride : 0);
   };
   ops.push_back(std::move(op));
 }

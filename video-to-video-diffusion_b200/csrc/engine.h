@@ -87,6 +87,14 @@ int load_gn(GNW& g, const WeightMap& wm, const std::string& prefix, int C, int G
 int load_conv(ConvLayer& L, int kind, const WeightMap& wm, const std::string& prefix, int cin0, int cin1, int cout);
 int groups32(int C);  // reference _get_num_groups: largest of 32,16,8,4,2,1 dividing C
 
+// where gn_apply finds the per-block time-embedding projections; read at launch (= graph capture) time
+struct TembSource {
+  const float* base = nullptr;   // [sample or step][rows]
+  int sample_stride = 0;         // per-sample stride (0: all samples share one row)
+  const int* step_ptr = nullptr; // device step counter selecting the row block (sampler graphs), or null
+  long long step_stride = 0;
+};
+
 // activation handle (batch is a property of the program)
 struct Act {
   __half* p = nullptr;
@@ -102,6 +110,7 @@ struct Builder {
   float* stats_base;
   size_t stats_cap, stats_used = 0;
   bool ok = true;
+  const TembSource* temb_src = nullptr;  // U-Net programs only
   Builder(std::vector<Op>& o, Pool& p, int b, float* sb, size_t sc) : ops(o), pool(p), B(b), stats_base(sb), stats_cap(sc) {}
   Act alloc(int C, int D, int H, int W);
   void free(Act& a);
@@ -109,8 +118,9 @@ struct Builder {
   // out_fp32 != nullptr: NCDHW fp32 head; otherwise returns a fresh cl16 activation
   Act conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, float* stats, int groups,
            float* out_fp32 = nullptr, int act = ACT_NONE, const float* bias_override = nullptr);
-  void gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, const float* temb,
-                int temb_stride, const Act* res, int mode, float* stats_out, int G_out);
+  // temb_off >= 0: add row offset temb_off of the time-embedding table (*temb_src) after the SiLU (mode 0)
+  void gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, int temb_off, const Act* res,
+                int mode, float* stats_out, int G_out);
 };
 
 }  // namespace b2v

@@ -13,6 +13,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // Programmatic dependent launch is wired through every kernel but OFF by default: inside the CUDA graphs the
 // kernel-to-kernel gap is already negligible and the measured step time was 0.5 % worse with it (16.53 vs 16.44 ms).
+void ew_set_round_bf16(int on) { cudaMemcpyToSymbol(c_round_bf16, &on, sizeof(int)); }
+
 bool pdl_enabled() {
   static const bool on = getenv("B2V_PDL") != nullptr;
   return on;
@@ -44,7 +46,7 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
   uint4 u;
   __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(operand_round(f[2 * i]), operand_round(f[2 * i + 1]));
   return u;
 }
 
@@ -60,8 +62,9 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
 template <int U, int MODE, bool STATS>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half* out_, const float* __restrict__ stats_in,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ temb, int temb_stride, const __half* res_, long long S,
-                                int C, int G, float eps, float* stats_out, int G_out) {
+                                const float* __restrict__ temb, int temb_stride, const int* __restrict__ temb_step,
+                                long long temb_step_stride, const __half* res_, long long S, int C, int G, float eps,
+                                float* stats_out, int G_out) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // [2*C] when stats_out
@@ -74,6 +77,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half*
   const int cpg = C / G;
   const float inv_n = 1.0f / ((float)S * (float)cpg);
 
+  // sampler graphs read the time-embedding projections of ALL steps from one table, indexed by the device step counter
+  const long long toff = (MODE == 0 && temb_step) ? (long long)(*temb_step) * temb_step_stride : 0;
   float sc[8], sh[8], ta[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half*
     const float ga = gamma[c];
     sc[j] = ga * rstd;
     sh[j] = beta[c] - mean * ga * rstd;
-    ta[j] = (MODE == 0 && temb) ? temb[(size_t)b * temb_stride + c] : 0.f;
+    ta[j] = (MODE == 0 && temb) ? temb[toff + (size_t)b * temb_stride + c] : 0.f;
   }
   float as[8], ass[8];
 #pragma unroll
@@ -170,7 +175,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half*
 
 void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const float* gamma, const float* beta,
                      const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
-                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st) {
+                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st, const int* temb_step,
+                     long long temb_step_stride) {
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
   const int threads = C8 * R;
@@ -182,7 +188,7 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
   const size_t smem = stats_out ? 2 * C * sizeof(float) : 0;
 #define GN_LAUNCH(UU, MM, SS)                                                                                     \
   launch_k(gn_apply_kernel<UU, MM, SS>, dim3(dim3(blocks, B)), dim3(threads), smem, st, y, out, stats_in, gamma, beta, temb, temb_stride, \
-                                                                      res, S, C, G, eps, stats_out, G_out)
+           temb_step, temb_step_stride, res, S, C, G, eps, stats_out, G_out)
 #define GN_DISPATCH(UU)                       \
   do {                                        \
     if (mode == 0) {                          \
@@ -257,30 +263,37 @@ void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* s
 // (the C x C product Wp*Wv and the folded bias are built once at weight-load time; the tiny GEMM runs on
 //  the conv kernel); add_bcast_t: x[b,t,p,:] += y[b,p,:].
 // ------------------------------------------------------------------------------------------------
+// one block per (sample, spatial position); thread = (8-channel vector, depth split): the T slices are shared
+// among blockDim/C8 thread groups (was one thread per column walking all T slices: latency-bound at 1.5 TB/s)
 __global__ void attn_tsum_kernel(const __half* __restrict__ x_, const float* __restrict__ stats,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, __half* s_, int T,
-                                 int P, int C, int G, float eps, long long total) {
+                                 int P, int C, int G, float eps) {
   pdl_trigger();
   pdl_wait();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  extern __shared__ float sm[];  // [TS][C]
   const int C8 = C >> 3;
-  const int cv = (int)(i % C8);
-  const long long bp = i / C8;
-  const int p = (int)(bp % P);
-  const int b = (int)(bp / P);
+  const int TS = blockDim.x / C8;
+  const int cv = threadIdx.x % C8, ts = threadIdx.x / C8;
+  const int p = blockIdx.x % P, b = blockIdx.x / P;
   const uint4* x = reinterpret_cast<const uint4*>(x_) + ((size_t)b * T * P + p) * C8 + cv;
+  const size_t tstride = (size_t)P * C8;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const size_t tstride = (size_t)P * C8;
 #pragma unroll 4
-  for (int t = 0; t < T; ++t) {
+  for (int t = ts; t < T; t += TS) {
     float f[8];
     h8_to_f(x[t * tstride], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += f[j];
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ts * C + cv * 8 + j] = acc[j];
+  __syncthreads();
+  if (ts != 0) return;
+  for (int k = 1; k < TS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += sm[k * C + cv * 8 + j];
   const int cpg = C / G;
   const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
   float o[8];
@@ -293,13 +306,17 @@ __global__ void attn_tsum_kernel(const __half* __restrict__ x_, const float* __r
     const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
     o[j] = gamma[c] * rstd * (acc[j] - (float)T * mean) + (float)T * beta[c];
   }
-  reinterpret_cast<uint4*>(s_)[i] = f_to_h8(o);
+  reinterpret_cast<uint4*>(s_)[((size_t)b * P + p) * C8 + cv] = f_to_h8(o);
 }
 
 void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
                       int T, int P, int C, int G, float eps, cudaStream_t st) {
-  const long long total = (long long)B * P * (C / 8);
-  launch_k(attn_tsum_kernel, dim3(cdiv(total, 128)), dim3(128), 0, st, x, stats, gamma, beta, s, T, P, C, G, eps, total);
+  const int C8 = C / 8;
+  int TS = 256 / C8;
+  if (TS < 1) TS = 1;
+  if (TS > T) TS = T;
+  launch_k(attn_tsum_kernel, dim3(B * P), dim3(C8 * TS), (size_t)TS * C * sizeof(float), st, x, stats, gamma, beta, s,
+           T, P, C, G, eps);
 }
 
 __global__ void add_bcast_t_kernel(__half* x_, const __half* __restrict__ y_, int T, long long PC8, long long total) {
@@ -713,7 +730,7 @@ __global__ void nc32_to_cl16_kernel(const float* __restrict__ in, __half* out, i
   if (i >= total) return;
   const int c = (int)(i % Cpad);
   const long long sp = (i / Cpad) % S, b = i / (Cpad * S);
-  out[i] = __float2half_rn(c < C ? in[((size_t)b * C + c) * S + sp] : 0.f);
+  out[i] = __float2half_rn(operand_round(c < C ? in[((size_t)b * C + c) * S + sp] : 0.f));
 }
 __global__ void cl16_to_nc32_kernel(const __half* __restrict__ in, float* out, int C, int Cpad, long long S,
                                     long long total) {

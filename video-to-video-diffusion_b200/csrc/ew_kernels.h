@@ -6,7 +6,8 @@ namespace b2v {
 
 void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const float* gamma, const float* beta,
                      const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
-                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st);
+                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st,
+                     const int* temb_step = nullptr, long long temb_step_stride = 0);
 void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st);
 void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
                       int T, int P, int C, int G, float eps, cudaStream_t st);
@@ -21,6 +22,7 @@ struct Coef8 {
 };
 void launch_ddpm_update(float* z, const float* eps, const float* noise, const Coef8& coef, long long n,
                         cudaStream_t st);
+void ew_set_round_bf16(int on);
 void launch_advance_step(int* step, cudaStream_t st);
 void launch_zero(float* p, long long n, cudaStream_t st);
 void launch_set_t(long long* t_dev, const long long* t_table, const int* step, long long imm, int B, cudaStream_t st);

@@ -181,6 +181,23 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---------------------------------------------------------------- operand-precision study (B2V_OPERANDS=bf16)
+// north_star names BF16; SURVEY F10 predicts BF16 operands miss the 1e-2 parity gate.  To MEASURE that on the B200
+// without a second kernel family, every value that becomes an MMA operand (activations at store time, weights at
+// pack time) can be rounded to BF16's 8-bit significand before it is stored in its fp16 container: the tensor core
+// then multiplies exactly the numbers a kind::f16 BF16 MMA would (same rate, fp32 accumulate).  Off by default.
+#ifdef __CUDACC__
+static __constant__ int c_round_bf16 = 0;
+__device__ __forceinline__ float operand_round(float x) {
+  if (c_round_bf16) {
+    uint32_t u = __float_as_uint(x);
+    u += 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even at bit 16
+    return __uint_as_float(u & 0xFFFF0000u);
+  }
+  return x;
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

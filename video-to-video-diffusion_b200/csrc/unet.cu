@@ -175,7 +175,7 @@ struct UBuild {
   UNet& u;
   UProgram& up;
   Builder b;
-  UBuild(UNet& u_, UProgram& p) : u(u_), up(p), b(p.core, p.pool, p.B, p.stats, p.stats_cap) {}
+  UBuild(UNet& u_, UProgram& p) : u(u_), up(p), b(p.core, p.pool, p.B, p.stats, p.stats_cap) { b.temb_src = &p.temb; }
 
   // ResBlock3D.forward (models/unet3d.py:116-133)
   Act res(const std::string& name, const ResW& r, const Act& x, const Act* skip, float** out_stats, int G_out) {
@@ -183,13 +183,13 @@ struct UBuild {
     Act y1 = b.conv(name + ".conv1", r.conv1, x, skip, s1, r.n1.G);
     Act rr;
     if (r.has_res) rr = b.conv(name + ".residual_conv", r.res, x, skip, nullptr, 0);
-    b.gn_apply(name + ".gn1_silu_temb", y1, s1, r.n1, up.proj + r.temb_off, u.proj_rows, nullptr, 0, nullptr, 0);
+    b.gn_apply(name + ".gn1_silu_temb", y1, s1, r.n1, r.temb_off, nullptr, 0, nullptr, 0);
     float* s2 = b.new_stats(r.n2.G);
     Act y2 = b.conv(name + ".conv2", r.conv2, y1, nullptr, s2, r.n2.G);
     b.free(y1);
     float* so = out_stats ? b.new_stats(G_out) : nullptr;
     if (out_stats) *out_stats = so;
-    b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, nullptr, 0, r.has_res ? &rr : &x, 1, so, G_out);
+    b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, -1, r.has_res ? &rr : &x, 1, so, G_out);
     if (r.has_res) b.free(rr);
     return y2;
   }
@@ -238,6 +238,7 @@ static int build_unet_program(UNet& u, UProgram& up) {
     if ((h >> l) & 1 || (w >> l) & 1) return fail("latent H, W must be divisible by 2^(levels-1)");
   const long long numel = (long long)B * L * T * h * w;
   up.numel = numel;
+  up.desc_rows = u.proj_rows;
   up.x_in = (float*)up.ds.alloc(numel * 4);
   up.c_in = (float*)up.ds.alloc(numel * 4);
   up.eps = (float*)up.ds.alloc(numel * 4);
@@ -365,23 +366,16 @@ static int build_unet_program(UNet& u, UProgram& up) {
   }
   if (!b.ok) return -1;
   // conv_out: GroupNorm -> SiLU -> Conv3d (models/unet3d.py:328-332)
-  b.gn_apply("conv_out.gn_silu", cur, cur_stats, u.out_norm, nullptr, 0, nullptr, 0, nullptr, 0);
+  b.gn_apply("conv_out.gn_silu", cur, cur_stats, u.out_norm, -1, nullptr, 0, nullptr, 0);
   b.conv("conv_out.conv", u.conv_out, cur, nullptr, nullptr, 0, up.eps);
   b.free(cur);
   if (!b.ok) return -1;
 
   up.fwd.ops = up.core;
   // sampler step: t from the table, core, DDIM update, advance
-  {
-    long long* td_ = up.t_dev;
-    const long long* tt = up.t_table;
-    const int* sp = up.step_dev;
-    Op op;
-    op.name = "set_t";
-    op.run = [=](cudaStream_t st) { launch_set_t(td_, tt, sp, 0, B, st); };
-    up.ddim.ops.push_back(std::move(op));
-  }
-  for (auto& o : up.core) up.ddim.ops.push_back(o);
+  // (the time embedding of every step is computed once per sample() call: see ddim_sample)
+  for (auto& o : up.core)
+    if (o.name != "time_embed") up.ddim.ops.push_back(o);
   {
     float* z = up.x_in;
     const float* e = up.eps;
@@ -409,7 +403,10 @@ UProgram* UNet::program(int B, int T, int h, int w) {
     last = it->second.get();
     return last;
   }
-  if (progs.size() >= 4) progs.clear();  // bound memory: shapes rarely change within a job
+  if (progs.size() >= 4) {  // bound memory: shapes rarely change within a job
+    progs.clear();
+    last = active = nullptr;
+  }
   std::unique_ptr<UProgram> up(new UProgram());
   up->B = B;
   up->T = T;
@@ -429,6 +426,7 @@ int UNet::forward(const float* x, const long long* t, const float* c, float* eps
   B2V_CUDA(cudaMemcpyAsync(up->x_in, x, bytes, cudaMemcpyDeviceToDevice, st));
   B2V_CUDA(cudaMemcpyAsync(up->c_in, c, bytes, cudaMemcpyDeviceToDevice, st));
   B2V_CUDA(cudaMemcpyAsync(up->t_dev, t, sizeof(long long) * B, cudaMemcpyDeviceToDevice, st));
+  up->temb = TembSource{up->proj, proj_rows, nullptr, 0};
   if (up->fwd.run(st)) return -1;
   B2V_CUDA(cudaMemcpyAsync(eps_out, up->eps, bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -470,6 +468,25 @@ int UNet::ddim_sample(const float* z_init, const float* cond, float* z_out, int 
   // pageable-host copies are staged by the runtime before returning, so the vectors may go out of scope
   B2V_CUDA(cudaMemcpyAsync(up->t_table, ts.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
   B2V_CUDA(cudaMemcpyAsync(up->coef_table, coef.data(), sizeof(float) * 8 * n, cudaMemcpyHostToDevice, st));
+  if (eta <= 0.f) {
+    // time embedding + all 22 block projections for every step at once ([n][rows] table, one launch pair)
+    if (up->all_cap < n) {
+      up->silu_all = (float*)up->ds.alloc((size_t)n * desc.time_embed_dim * sizeof(float));
+      up->proj_all = (float*)up->ds.alloc((size_t)n * proj_rows * sizeof(float));
+      if (!up->silu_all || !up->proj_all) return fail("out of device memory (time-embedding table)");
+      up->all_cap = n;
+      if (up->ddim.exec) {  // the captured graph holds the old table pointer
+        cudaGraphExecDestroy(up->ddim.exec);
+        up->ddim.exec = nullptr;
+      }
+    }
+    launch_temb(up->t_table, nullptr, nullptr, freqs, W1, B1, W2, B2, up->silu_all, Wproj, Bproj, up->proj_all,
+                proj_rows, desc.model_channels, desc.time_embed_dim, n, st);
+    g_launches += 2;
+    up->temb = TembSource{up->proj_all, 0, up->step_dev, proj_rows};
+  } else {
+    up->temb = TembSource{up->proj, proj_rows, nullptr, 0};
+  }
   for (int i = 0; i < n; ++i) {
     if (eta > 0.f) {
       // stochastic variant: the update needs this step's noise pointer, so it runs outside the step graph
@@ -492,6 +509,7 @@ int UNet::ddpm_step(long long t, const float* coef, const float* noise, cudaStre
   UProgram* up = active;
   if (!up) return fail("ddpm_step: call b2v_sampler_begin first");
   launch_set_t(up->t_dev, nullptr, nullptr, t, up->B, st);
+  up->temb = TembSource{up->proj, proj_rows, nullptr, 0};
   if (up->fwd.run(st)) return -1;
   Coef8 c8;
   for (int i = 0; i < 8; ++i) c8.v[i] = coef[i];

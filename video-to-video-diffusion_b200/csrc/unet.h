@@ -37,6 +37,10 @@ struct UProgram {
   int *step_dev = nullptr, *nan_dev = nullptr;
   float *coef_table = nullptr, *stats = nullptr, *silu_temb = nullptr, *proj = nullptr;
   size_t stats_cap = 0;
+  TembSource temb;            // set before every run: per-sample table (forward) or all-steps table (DDIM graph)
+  float *silu_all = nullptr, *proj_all = nullptr;  // time embedding of every DDIM step, computed once per sample() call
+  int all_cap = 0;
+  int desc_rows = 0;  // rows of one time-embedding projection table (= UNet::proj_rows)
 };
 
 struct UNet {

@@ -97,18 +97,18 @@ struct VBuild {
     float* s = b.new_stats(8);
     Act y = b.conv(name + ".conv", w.conv, x, nullptr, s, 8);
     b.free(x);
-    b.gn_apply(name + ".gn_silu", y, s, w.norm, nullptr, 0, nullptr, 0, nullptr, 0);
+    b.gn_apply(name + ".gn_silu", y, s, w.norm, -1, nullptr, 0, nullptr, 0);
     return y;
   }
   // models/vae.py:50-56 ; consumes x
   Act res(const std::string& name, const VResW& r, Act& x) {
     float* s1 = b.new_stats(8);
     Act y1 = b.conv(name + ".conv1", r.conv1, x, nullptr, s1, 8);
-    b.gn_apply(name + ".gn1_silu", y1, s1, r.n1, nullptr, 0, nullptr, 0, nullptr, 0);
+    b.gn_apply(name + ".gn1_silu", y1, s1, r.n1, -1, nullptr, 0, nullptr, 0);
     float* s2 = b.new_stats(8);
     Act y2 = b.conv(name + ".conv2", r.conv2, y1, nullptr, s2, 8);
     b.free(y1);
-    b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, nullptr, 0, &x, 1, nullptr, 0);
+    b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, -1, &x, 1, nullptr, 0);
     b.free(x);
     return y2;
   }
