@@ -107,6 +107,11 @@ int b2v_stitch_accumulate(const float* patch, float* acc, float* wsum, const flo
                           void* stream);
 int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* stream);
 
+/* utils/metrics.py:125-193  calculate_video_metrics: a, b (BC, T, H, W) fp32 in [0, max_val]; out: DEVICE fp32 [T][2]
+ * = per depth slice (sum of squared error, sum of the 11x11 box-filter SSIM map) over all (bc, h, w)           */
+int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
+                      void* stream);
+
 /* per-op timing of the last planned program of an object, written as JSON text into buf:
  *   [{"name": "...", "ms": .., "flops": .., "bytes": ..}, ...]  (averaged over iters CUDA-event-timed runs)   */
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream);

@@ -334,3 +334,22 @@ def psnr(a, b, max_val=1.0):
     """utils/metrics.py:14-44 calculate_psnr, on tensors already mapped to [0, 1]"""
     mse = torch.clamp(torch.mean((a - b) ** 2), min=1e-8)
     return float(torch.clamp(20 * torch.log10(max_val / torch.sqrt(mse)), 0.0, 100.0))
+
+
+def ssim(img1, img2, max_val=1.0):
+    """calculate_ssim for a 4-D (B,C,H,W) pair (utils/metrics.py:84-122): 11x11 box filter, zero padding"""
+    C1, C2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    pool = lambda x: F.avg_pool2d(x, 11, stride=1, padding=5)  # noqa: E731
+    mu1, mu2 = pool(img1), pool(img2)
+    s1 = torch.clamp(pool(img1 ** 2) - mu1 ** 2, min=0.0)
+    s2 = torch.clamp(pool(img2 ** 2) - mu2 ** 2, min=0.0)
+    s12 = pool(img1 * img2) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 ** 2 + mu2 ** 2 + C1) * (s1 + s2 + C2) + 1e-8)
+    return float(torch.clamp(m, 0.0, 1.0).mean())
+
+
+def video_metrics(v1, v2, max_val=1.0):
+    """calculate_video_metrics (utils/metrics.py:125-193): per depth slice PSNR / SSIM over (B,C,H,W), then the means"""
+    ps = [psnr(v1[:, :, t], v2[:, :, t], max_val) for t in range(v1.shape[2])]
+    ss = [ssim(v1[:, :, t], v2[:, :, t], max_val) for t in range(v1.shape[2])]
+    return {"psnr": sum(ps) / len(ps), "ssim": sum(ss) / len(ss), "psnr_per_frame": ps, "ssim_per_frame": ss}

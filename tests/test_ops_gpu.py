@@ -185,3 +185,22 @@ def test_stitch_kernels_match_reference_blend(cuda_dev):
     got = ops.stitch_normalize(acc, ws)
     assert torch.equal(got, ref), (got - ref).abs().max().item()
     assert abs(ops.gaussian_window_1d(48, cuda_dev).cpu() - R.gaussian_weight(48, 1, 1)[:, 0, 0]).max() == 0
+
+
+def test_video_metrics_kernel_matches_reference_definition(cuda_dev):
+    """per-slice PSNR and 11x11 box-filter SSIM (utils/metrics.py) from one fused kernel"""
+    from oracle import ref_port as R
+    from v2v_b200.utils import calculate_psnr, calculate_ssim, calculate_video_metrics
+    g = torch.Generator().manual_seed(33)
+    a = torch.rand((2, 1, 5, 70, 45), generator=g).to(cuda_dev)
+    b = (a + 0.05 * torch.randn((2, 1, 5, 70, 45), generator=g).to(cuda_dev)).clamp(0, 1)
+    got, ref = calculate_video_metrics(a, b, max_val=1.0), R.video_metrics(a, b)
+    assert abs(got["psnr"] - ref["psnr"]) < 1e-3 and abs(got["ssim"] - ref["ssim"]) < 1e-4
+    assert max(abs(x - y) for x, y in zip(got["psnr_per_frame"], ref["psnr_per_frame"])) < 1e-3
+    assert max(abs(x - y) for x, y in zip(got["ssim_per_frame"], ref["ssim_per_frame"])) < 1e-4
+    assert abs(calculate_ssim(a, b) - ref["ssim"]) < 1e-4
+    assert abs(calculate_psnr(a[:, :, 0], b[:, :, 0]) - ref["psnr_per_frame"][0]) < 1e-3
+    assert calculate_video_metrics(a, a)["psnr"] == 80.0  # mse clamped at 1e-8 -> 80 dB, as in the reference
+    bad = a.clone()
+    bad[0, 0, 0, 0, 0] = float("nan")
+    assert calculate_video_metrics(bad, b) == {"psnr": 0.0, "ssim": 0.0, "psnr_per_frame": [], "ssim_per_frame": []}

@@ -177,6 +177,16 @@ int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* strea
   return 0;
 }
 
+int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
+                       void* stream) {
+  if (check_device()) return -1;
+  B2V_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 2 * T, (cudaStream_t)stream));
+  launch_video_metrics(a, b, out, BC, T, H, W, max_val, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* bias, int cin0, int cin1, int cout) {
   if (check_device()) return -1;
   std::string err;

@@ -720,6 +720,95 @@ void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Caller-side quality metrics (reference utils/metrics.py:14-193, what Trainer.validate* runs after generate()):
+// per depth slice t, over all (b, c, h, w):  sum of squared error  and  sum of the box-filter SSIM map
+//   mu = avg_pool2d(x, 11, stride 1, pad 5) (zero padding, divisor 121), sigma^2 = E[x^2]-mu^2 clamped at 0,
+//   ssim = clamp(((2 mu1 mu2 + C1)(2 s12 + C2)) / ((mu1^2 + mu2^2 + C1)(s1 + s2 + C2) + 1e-8), 0, 1)
+// One block = a 32x32 output tile of one (b, c, t) plane; the 42x42 halo tiles of both images sit in shared memory,
+// the 11x11 box sums of the five moments are separable.  out[t] += (sq_err, ssim) with one atomic pair per block;
+// the reference does two .item() host syncs per slice instead.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) video_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            float* out, int T, int H, int W, float C1, float C2) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int TS = 32, R = 5, IN = TS + 2 * R;  // 42
+  __shared__ float sa[IN][IN + 1], sb[IN][IN + 1];
+  __shared__ float hs[5][IN][TS + 1];
+  __shared__ float red[2][8];
+  const int plane = blockIdx.z;  // (b*C + c)*T + t
+  const int t = plane % T;
+  const float* pa = a + (size_t)plane * H * W;
+  const float* pb = b + (size_t)plane * H * W;
+  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  for (int i = threadIdx.x; i < IN * IN; i += 256) {
+    const int ly = i / IN, lx = i % IN;
+    const int gy = y0 + ly - R, gx = x0 + lx - R;
+    const bool in = (gy >= 0 && gy < H && gx >= 0 && gx < W);
+    sa[ly][lx] = in ? pa[(size_t)gy * W + gx] : 0.f;
+    sb[ly][lx] = in ? pb[(size_t)gy * W + gx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < IN * TS; i += 256) {  // horizontal 11-tap sums of x, y, xx, yy, xy
+    const int ly = i / TS, lx = i % TS;
+    float s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; ++k) {
+      const float u = sa[ly][lx + k], v = sb[ly][lx + k];
+      s0 += u;
+      s1 += v;
+      s2 += u * u;
+      s3 += v * v;
+      s4 += u * v;
+    }
+    hs[0][ly][lx] = s0;
+    hs[1][ly][lx] = s1;
+    hs[2][ly][lx] = s2;
+    hs[3][ly][lx] = s3;
+    hs[4][ly][lx] = s4;
+  }
+  __syncthreads();
+  float se = 0.f, ssim = 0.f;
+  for (int i = threadIdx.x; i < TS * TS; i += 256) {
+    const int ly = i / TS, lx = i % TS;
+    if (y0 + ly < H && x0 + lx < W) {
+      float m[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 2 * R + 1; ++k)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) m[q] += hs[q][ly + k][lx];
+      const float inv = 1.0f / 121.0f;
+      const float mu1 = m[0] * inv, mu2 = m[1] * inv;
+      const float s1 = fmaxf(m[2] * inv - mu1 * mu1, 0.f), s2 = fmaxf(m[3] * inv - mu2 * mu2, 0.f);
+      const float s12 = m[4] * inv - mu1 * mu2;
+      const float num = (2.f * mu1 * mu2 + C1) * (2.f * s12 + C2);
+      const float den = (mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2) + 1e-8f;
+      ssim += fminf(fmaxf(num / den, 0.f), 1.f);
+      const float d = sa[ly + R][lx + R] - sb[ly + R][lx + R];
+      se += d * d;
+    }
+  }
+  se = warp_sum(se);
+  ssim = warp_sum(ssim);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = se;
+    red[1][threadIdx.x >> 5] = ssim;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
+    atomicAdd(out + t * 2 + threadIdx.x, s);
+  }
+}
+void launch_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
+                          cudaStream_t st) {
+  const float C1 = (0.01f * max_val) * (0.01f * max_val), C2 = (0.03f * max_val) * (0.03f * max_val);
+  launch_k(video_metrics_kernel, dim3((W + 31) / 32, (H + 31) / 32, BC * T), dim3(256), 0, st, a, b, out, T, H, W, C1,
+           C2);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout casts for the op-level API and tests
 // ------------------------------------------------------------------------------------------------
 __global__ void nc32_to_cl16_kernel(const float* __restrict__ in, __half* out, int C, int Cpad, long long S,

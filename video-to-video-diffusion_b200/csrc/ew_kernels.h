@@ -39,6 +39,8 @@ void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const
                               const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
                               int w0, cudaStream_t st);
 void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStream_t st);
+void launch_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
+                          cudaStream_t st);
 void launch_nc32_to_cl16(const float* in, __half* out, int B, int C, int Cpad, long long S, cudaStream_t st);
 void launch_cl16_to_nc32(const __half* in, float* out, int B, int C, int Cpad, long long S, cudaStream_t st);
 
