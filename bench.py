@@ -175,8 +175,8 @@ def ncu_traffic():
         return None
     with open(p) as f:
         d = json.load(f)
-    return {"dram_bytes_per_launch": d["dram_bytes_read"] + d["dram_bytes_write"],
-            "algorithmic_bytes_per_launch": sum(d["algorithmic_bytes"].values()), "launch": d["source"]}
+    return d["dram_bytes_read"] + d["dram_bytes_write"], {
+        "algorithmic_bytes_per_launch": sum(d["algorithmic_bytes"].values()), "launch": d["source"], "note": d["note"]}
 
 
 def roofline_from_profile(prof, pk):
@@ -198,7 +198,7 @@ def roofline_from_profile(prof, pk):
             "share_of_step": round(sum(o["ms"] for o in convs) / max(1e-9, sum(t_all.values())), 4),
             "slowest_launch": {"name": top["name"], "ms": round(top["ms"], 4),
                                "tflops": round(top["flops"] / top["ms"] / 1e9, 1)},
-            "traffic": ncu_traffic(),
+            "traffic": (ncu_traffic() or (None, None))[0], "traffic_detail": (ncu_traffic() or (None, None))[1],
             "hbm_kernels": {"achieved_gbs": round(b_ew / t_ew / 1e9, 1) if t_ew > 0 else None,
                             "peak_gbs": pk["hbm_gbs"], "frac": round(b_ew / t_ew / 1e9 / pk["hbm_gbs"], 4) if t_ew > 0 else None,
                             "note": "GroupNorm-apply / pack / attention-sum kernels, algorithmic bytes / event time"},

@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # libb2v.so is a build artefact (git-ignored): build it on a fresh checkout so the suite is self-contained
+    lib = os.path.join(ROOT, "video-to-video-diffusion_b200", "libb2v.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "video-to-video-diffusion_b200", "csrc"), "-j8"], check=True,
+                       stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
