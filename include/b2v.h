@@ -112,6 +112,12 @@ int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* strea
 int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
                       void* stream);
 
+/* data/patch_slice_interpolation_dataset.py:163-181 + data/slice_interpolation_dataset.py:575-592, on the device:
+ * crop [z0,z1) x [y0,y0+ph) x [x0,x0+pw) of vol (D,H,W), apply f(v) = a*clip(v,lo,hi)+b (CT windowing / range map),
+ * resample the depth axis to pd slices like F.interpolate(trilinear, align_corners=False); out: (pd,ph,pw)      */
+int b2v_extract_patch(const float* vol, float* out, int D, int H, int W, int z0, int z1, int y0, int x0, int pd, int ph,
+                      int pw, float lo, float hi, float a, float b, void* stream);
+
 /* per-op timing of the last planned program of an object, written as JSON text into buf:
  *   [{"name": "...", "ms": .., "flops": .., "bytes": ..}, ...]  (averaged over iters CUDA-event-timed runs)   */
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream);

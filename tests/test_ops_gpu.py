@@ -204,3 +204,27 @@ def test_video_metrics_kernel_matches_reference_definition(cuda_dev):
     bad = a.clone()
     bad[0, 0, 0, 0, 0] = float("nan")
     assert calculate_video_metrics(bad, b) == {"psnr": 0.0, "ssim": 0.0, "psnr_per_frame": [], "ssim_per_frame": []}
+
+
+def test_input_side_patch_extraction_and_windowing(cuda_dev):
+    """aligned crop + depth resample + CT windowing vs the reference's torch/numpy formulation"""
+    from v2v_b200.utils.inputs import apply_ct_windowing, extract_thick_patch
+    g = torch.Generator().manual_seed(41)
+    thick = torch.randn((1, 50, 64, 80), generator=g).to(cuda_dev)
+    for (zs, ze, y0, x0) in [(0, 48, 0, 0), (100, 148, 10, 20), (252, 300, 32, 48), (13, 14, 5, 5)]:
+        D_thin = 300
+        got = extract_thick_patch(thick, zs, ze, D_thin, y0, x0, 8, (32, 32))
+        a, b = int(zs * 50 / D_thin), int(ze * 50 / D_thin)
+        b = max(b, a + 1)
+        sub = thick[:, max(0, a):min(50, b), y0:y0 + 32, x0:x0 + 32]
+        ref = F.interpolate(sub.unsqueeze(0), size=(8, 32, 32), mode="trilinear", align_corners=False).squeeze(0)
+        assert got.shape == ref.shape == (1, 8, 32, 32)
+        assert (got - ref).abs().max().item() < 1e-5
+    hu = (torch.randn((6, 40, 40), generator=g) * 400).to(cuda_dev)
+    lower, upper = 40 - 400 / 2, 40 + 400 / 2
+    ref = (torch.clamp(hu, lower, upper) - lower) / (upper - lower)
+    assert (apply_ct_windowing(hu, 40, 400) - ref).abs().max().item() < 1e-6
+    pm1 = extract_thick_patch(hu, 0, 6, 6, 0, 0, 6, (40, 40), window=(40, 400), to_pm1=True)[0]
+    assert (pm1 - (ref * 2 - 1)).abs().max().item() < 1e-6
+    with pytest.raises(RuntimeError):
+        extract_thick_patch(thick, 0, 48, 300, 40, 60, 8, (32, 32))  # window outside the volume

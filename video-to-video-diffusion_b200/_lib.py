@@ -58,6 +58,8 @@ SIGNATURES = {
                                       c_int, c_int, _P]),
     "b2v_stitch_normalize": (c_int, [_P, _P, c_longlong, _P]),
     "b2v_video_metrics": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    "b2v_extract_patch": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                  c_float, c_float, c_float, _P]),
     "b2v_unet_profile": (c_int, [_P, c_int, c_char_p, c_size_t, _P]),
     "b2v_vae_profile": (c_int, [_P, c_int, c_int, c_char_p, c_size_t, _P]),
     "b2v_debug_op_output": (c_longlong, [_P, c_int, c_int, c_int, _P, c_size_t, _P]),

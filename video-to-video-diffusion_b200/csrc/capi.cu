@@ -187,6 +187,17 @@ int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T,
   return 0;
 }
 
+int b2v_extract_patch(const float* vol, float* out, int D, int H, int W, int z0, int z1, int y0, int x0, int pd, int ph,
+                       int pw, float lo, float hi, float a, float b, void* stream) {
+  if (check_device()) return -1;
+  if (z0 < 0 || z1 > D || z1 <= z0 || y0 < 0 || x0 < 0 || y0 + ph > H || x0 + pw > W || pd < 1)
+    return fail("extract_patch: window outside the volume");
+  launch_extract_patch(vol, out, H, W, z0, z1 - z0, y0, x0, pd, ph, pw, lo, hi, a, b, (cudaStream_t)stream);
+  g_launches += 1;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int b2v_conv_create(b2v_conv** out, int kind, const float* weight, const float* bias, int cin0, int cin1, int cout) {
   if (check_device()) return -1;
   std::string err;

@@ -809,6 +809,39 @@ void launch_video_metrics(const float* a, const float* b, float* out, int BC, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input side (reference data/slice_interpolation_dataset.py:575-592 CT windowing, and
+// data/patch_slice_interpolation_dataset.py:163-181 aligned crop + depth resample of the thick sub-volume):
+//   out[d,h,w] = lerp_depth( f(vol[z0 + i, y0 + h, x0 + w]) ),  f(v) = a * clip(v, lo, hi) + b
+// with the depth source index of F.interpolate(trilinear, align_corners=False): src = n/pd * (d + 0.5) - 0.5 (>= 0).
+// One pass, coalesced along w; feeds the encoder directly on the device.
+// ------------------------------------------------------------------------------------------------
+__global__ void extract_patch_kernel(const float* __restrict__ vol, float* out, int H, int W, int z0, int n, int y0,
+                                     int x0, int pd, int ph, int pw, float lo, float hi, float a, float b,
+                                     long long total) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int w = (int)(i % pw), h = (int)((i / pw) % ph), d = (int)(i / ((long long)pw * ph));
+  const float scale = (float)n / (float)pd;
+  float src = scale * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  const int i0 = (int)src;
+  const int i1 = i0 + ((i0 < n - 1) ? 1 : 0);
+  const float l1 = src - (float)i0, l0 = 1.0f - l1;
+  const size_t plane = (size_t)H * W, off = (size_t)(y0 + h) * W + (x0 + w);
+  const float v0 = fminf(fmaxf(vol[(size_t)(z0 + i0) * plane + off], lo), hi) * a + b;
+  const float v1 = fminf(fmaxf(vol[(size_t)(z0 + i1) * plane + off], lo), hi) * a + b;
+  out[i] = l0 * v0 + l1 * v1;
+}
+void launch_extract_patch(const float* vol, float* out, int H, int W, int z0, int n, int y0, int x0, int pd, int ph,
+                          int pw, float lo, float hi, float a, float b, cudaStream_t st) {
+  const long long total = (long long)pd * ph * pw;
+  launch_k(extract_patch_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, vol, out, H, W, z0, n, y0, x0, pd, ph, pw,
+           lo, hi, a, b, total);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout casts for the op-level API and tests
 // ------------------------------------------------------------------------------------------------
 __global__ void nc32_to_cl16_kernel(const float* __restrict__ in, __half* out, int C, int Cpad, long long S,
