@@ -39,6 +39,11 @@ CONV_CASES = [
     ("upT_128_64", 3, 128, 0, 64, 2, 4, 6, 6),
     ("k3_waves", 0, 128, 0, 128, 2, 8, 48, 48),
     ("k3_odd", 0, 64, 0, 64, 1, 5, 7, 9),
+    # few output tiles, long K loops: the split-K path (fp32 vector atomics + finalize pass)
+    ("k3_splitk", 0, 512, 0, 512, 1, 6, 6, 6),
+    ("k3_dual_splitk", 0, 256, 256, 256, 1, 4, 6, 6),
+    ("down_splitk", 2, 128, 0, 256, 1, 4, 12, 12),
+    ("k3_splitk_b2", 0, 256, 0, 512, 2, 12, 6, 6),
 ]
 
 

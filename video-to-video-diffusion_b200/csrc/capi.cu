@@ -16,6 +16,8 @@ struct b2v_conv {
   ConvLayer L;
   float* ws = nullptr;  // tap-GEMM workspace of narrow heads (grown on demand)
   size_t ws_bytes = 0;
+  float* sk = nullptr;  // split-K workspace (zero between uses)
+  size_t sk_bytes = 0;
 };
 
 static int check_device() {
@@ -214,6 +216,7 @@ void b2v_conv_destroy(b2v_conv* c) {
   if (c) {
     conv_layer_free(c->L);
     if (c->ws) cudaFree(c->ws);
+    if (c->sk) cudaFree(c->sk);
   }
   delete c;
 }
@@ -230,11 +233,21 @@ int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, i
     B2V_CUDA(cudaMalloc(&c->ws, need_ws));
     c->ws_bytes = need_ws;
   }
+  const size_t need_sk = out_fp32 ? 0 : conv_splitk_ws_bytes(c->L, N, D, H, W);
+  if (need_sk > c->sk_bytes) {
+    B2V_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (c->sk) cudaFree(c->sk);
+    c->sk = nullptr;
+    c->sk_bytes = 0;
+    B2V_CUDA(cudaMalloc(&c->sk, need_sk));
+    B2V_CUDA(cudaMemset(c->sk, 0, need_sk));
+    c->sk_bytes = need_sk;
+  }
   if (conv_plan(P, c->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, out_fp32 ? OUT_F32 : OUT_CL16, stats,
-                groups, act_tanh ? ACT_TANH : ACT_NONE, err, need_ws ? c->ws : nullptr))
+                groups, act_tanh ? ACT_TANH : ACT_NONE, err, need_ws ? c->ws : nullptr, need_sk ? c->sk : nullptr))
     return fail(err);
   conv_launch(P, (cudaStream_t)stream);
-  g_launches += P.tapgemm ? 2 : 1;
+  g_launches += (P.tapgemm || P.splitk > 1) ? 2 : 1;
   B2V_CUDA(cudaGetLastError());
   return 0;
 }

@@ -281,6 +281,35 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
+static void out_grid(const ConvLayer& L, int D, int H, int W, int& gD, int& gH, int& gW) {
+  gD = D;
+  gH = (L.kind == CONV_DOWN) ? H / 2 : H;
+  gW = (L.kind == CONV_DOWN) ? W / 2 : W;
+}
+
+int conv_splitk_factor(const ConvLayer& L, int N, int D, int H, int W) {
+  static const bool off = getenv("B2V_NO_SPLITK") != nullptr;
+  if (off || L.bn < 64 || L.kind == CONV_UPT || L.cout % 8) return 1;
+  int gD, gH, gW, bw, bh, bd;
+  out_grid(L, D, H, W, gD, gH, gW);
+  choose_box(gW, gH, gD, bw, bh, bd);
+  const long long tiles = (long long)((gW + bw - 1) / bw) * ((gH + bh - 1) / bh) * ((gD + bd - 1) / bd) * N *
+                          (L.cout_pad / L.bn);
+  const int ksteps = L.ntaps * (L.cin0_pad + L.cin1_pad) / 64;
+  const int sms = device_sm_count();
+  if (tiles * 2 > sms || ksteps < 32) return 1;
+  int S = (int)(sms / tiles);
+  if (S > ksteps / 16) S = ksteps / 16;
+  if (S > 8) S = 8;
+  return S < 2 ? 1 : S;
+}
+size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
+  if (conv_splitk_factor(L, N, D, H, W) < 2) return 0;
+  int gD, gH, gW;
+  out_grid(L, D, H, W, gD, gH, gW);
+  return (size_t)N * gD * gH * gW * L.cout * sizeof(float);
+}
+
 static inline long long tap_pairs(long long positions) { return ((positions + 127) / 128 + 1) / 2; }
 
 size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
@@ -293,6 +322,7 @@ size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
 static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int N, int D, int H, int W, void* out,
                         int act, std::string& err, float* ws) {
   ConvParams& p = P.p;
+  p.splitk = 1;
   const long long pos = (long long)N * D * H * W;
   const long long pairs = tap_pairs(pos);
   p.bw = 128;
@@ -338,10 +368,13 @@ static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int 
 }
 
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws) {
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws,
+              float* splitk_ws) {
   memset(&P, 0, sizeof(P));
   ConvParams& p = P.p;
   P.bn = L.bn;
+  P.splitk = 1;
+  p.splitk = 1;
   if (tap_ws && out_mode == OUT_F32 && !in1 && !stats && conv_tap_ws_bytes(L, N, D, H, W))
     return plan_tapgemm(P, L, in0, N, D, H, W, out, act, err, tap_ws);
   if ((L.cin1 != 0) != (in1 != nullptr)) {
@@ -442,6 +475,22 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
   P.swapped = !no_swap && L.cout == 128 && L.bn == 128 && out_mode == OUT_CL16 && act == ACT_NONE &&
               (tiles_per_sample % 2 == 0) && (!stats || p.cpg <= 32);
   if (P.swapped) total /= 2;
+  if (splitk_ws && !P.swapped && out_mode == OUT_CL16 && act == ACT_NONE) {
+    const int S = conv_splitk_factor(L, N, D, H, W);
+    if (S > 1) {
+      P.splitk = p.splitk = S;
+      p.ws = splitk_ws;
+      total *= S;
+      P.fin.ws = splitk_ws;
+      P.fin.bias = L.bias;
+      P.fin.out = (__half*)out;
+      P.fin.stats = stats;
+      P.fin.S = (long long)gD * gH * gW;
+      P.fin.C = L.cout;
+      P.fin.G = groups ? groups : 1;
+      P.fin.B = N;
+    }
+  }
   P.grid = (int)(total < sms ? total : sms);
   const double taps_real = (L.kind == CONV_K1) ? 1 : (L.kind == CONV_DOWN || L.kind == CONV_UPT) ? 48 : 27;
   const double pos = (L.kind == CONV_UPT) ? (double)N * D * H * W : (double)N * gD * gH * gW;
@@ -459,6 +508,15 @@ void conv_launch(const ConvPlan& P, cudaStream_t st) {
   }
   if (P.swapped) {
     launch_k(conv_igemm_t_kernel<0>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
+    return;
+  }
+  if (P.splitk > 1) {
+    switch (P.bn) {
+      case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(192), ConvCfg<64>::SMEM, st, P.p); break;
+      case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
+      default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
+    }
+    launch_splitk_finalize(P.fin.ws, P.fin.bias, P.fin.out, P.fin.stats, P.fin.B, P.fin.S, P.fin.C, P.fin.G, st);
     return;
   }
   switch (P.bn) {

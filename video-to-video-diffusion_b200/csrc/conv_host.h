@@ -49,6 +49,16 @@ struct ConvPlan {
     int N, cout, D, H, W, act;
     long long row_stride;
   } st;
+  // split-K (small-M layers): the conv kernel adds fp32 partial tiles into fin.ws, fin describes the finalize pass
+  int splitk = 1;
+  struct {
+    float* ws;
+    const float* bias;
+    __half* out;
+    float* stats;
+    long long S;
+    int C, G, B;
+  } fin;
   double flops = 0;  // algorithmic 2*MAC of the reference convolution (no padding / packing waste)
 };
 
@@ -60,7 +70,11 @@ void conv_layer_free(ConvLayer& L);
 // in0/in1: NDHWC fp16 [N][D][H][W][cin*_pad]; (D,H,W) are the INPUT dims.
 // out_mode OUT_CL16: out is NDHWC fp16 with cout channels; OUT_F32: out is NCDHW fp32 with cout channels.
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws = nullptr);
+              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws = nullptr,
+              float* splitk_ws = nullptr);
+// k-split factor the planner would use for this layer / input (1 = none) and the fp32 workspace it needs
+int conv_splitk_factor(const ConvLayer& L, int N, int D, int H, int W);
+size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W);
 // bytes of fp32 workspace the tap-GEMM path of a narrow head needs for this input (0: layer has no such path)
 size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W);
 void conv_launch(const ConvPlan& P, cudaStream_t st);

@@ -28,10 +28,7 @@ struct ConvCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  // narrow heads (BN = 16): back-to-back MMAs into ONE accumulator are latency-bound (each waits for the previous
-  // one), so consecutive k-steps rotate over NSUB independent accumulators that the epilogue adds up
-  static constexpr int NSUB = (BN == 16) ? 4 : 1;
-  static constexpr int TM_COLS = (2 * BN * NSUB < 32) ? 32 : 2 * BN * NSUB;
+  static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*group stats*/;
 };
 
@@ -80,6 +77,15 @@ __device__ __forceinline__ void chunk_stats(const float* v, bool valid, float* s
   if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(&sstat[glocal * 2 + (lane >> (5 - LOG))], tot);
 }
 
+// Split-K for small-M layers (few output tiles, e.g. the 6x6 level at batch 1: 28 tiles on 148 SMs): work unit =
+// (tile, k-split); every unit accumulates its slice of the (tap, chunk) loop and adds its fp32 partial tile into a
+// zero-initialised workspace with vector atomics; splitk_finalize_kernel then applies bias, statistics and the fp16
+// conversion (and re-zeroes the workspace).  splitk == 1 is the ordinary path.
+__device__ __forceinline__ int unit_k0(int unit, int ksteps, int S) { return (int)((long long)(unit % S) * ksteps / S); }
+__device__ __forceinline__ int unit_k1(int unit, int ksteps, int S) {
+  return (int)((long long)(unit % S + 1) * ksteps / S);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
   const int total_tiles = m_tiles * p.nclass * p.n_tiles;
+  const int total_units = total_tiles * p.splitk;
   const int chunks = p.src_chunks0 + p.src_chunks1;
 
   if (threadIdx.x == 0) {
@@ -131,7 +138,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       const uint32_t a_bytes = (uint32_t)p.rows_valid * 128u;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ksteps = p.ntaps * chunks;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int tile = unit / p.splitk;
         int m = tile % m_tiles;
         int rest = tile / m_tiles;
         const int cls = rest % p.nclass;
@@ -142,25 +151,29 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         m /= p.tiles_h;
         const int d0 = (m % p.tiles_d) * p.bd;
         const int nb = m / p.tiles_d;
-        for (int t = 0; t < p.ntaps; ++t) {
+        const int k0 = unit_k0(unit, ksteps, p.splitk), k1 = unit_k1(unit, ksteps, p.splitk);
+        int t = k0 / chunks, c = k0 % chunks;
+        for (int k = k0; k < k1; ++k) {
           const int tg = cls * p.ntaps + t;
           const int32_t tp = p.taps[tg];
           const int map = tp >> 24;
           const int cd = d0 + ((tp >> 16) & 0xff) - 8;
           const int chh = h0 + ((tp >> 8) & 0xff) - 8;
           const int cw = w0 + (tp & 0xff) - 8;
-          for (int c = 0; c < chunks; ++c) {
-            const int src = (c >= p.src_chunks0) ? 1 : 0;
-            const int cc = src ? (c - p.src_chunks0) : c;
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
-            uint8_t* sa = smem + stage * Cfg::STAGE;
-            tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
-            tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
-            if (++stage == NSTAGE) {
-              stage = 0;
-              phase ^= 1;
-            }
+          const int src = (c >= p.src_chunks0) ? 1 : 0;
+          const int cc = src ? (c - p.src_chunks0) : c;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE;
+          tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
+          tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++c == chunks) {
+            c = 0;
+            ++t;
           }
         }
       }
@@ -173,23 +186,22 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN * Cfg::NSUB);
-        for (int k = 0; k < ksteps; ++k) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        const int nk = unit_k1(unit, ksteps, p.splitk) - unit_k0(unit, ksteps, p.splitk);
+        for (int k = 0; k < nk; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
-          const uint32_t tmem_d = tmem_acc + (uint32_t)((k % Cfg::NSUB) * BN);
-          const bool first = (k < Cfg::NSUB);  // first k-step landing in this sub-accumulator
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (!first || kk) ? 1u : 0u);
+            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == NSTAGE) {
             stage = 0;
@@ -221,7 +233,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      const int tile = unit / p.splitk;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int m = tile % m_tiles;
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       const int nb = m / p.tiles_d;
       const bool valid = (r < p.rows_valid) && (w < p.W) && (h < p.H) && (d < p.D);
       const long long roff = p.cls_off[cls] + nb * p.sN + d * p.sD + h * p.sH + w * p.sW;
-      if (p.stats) {
+      if (p.stats && p.splitk == 1) {
         const int key = nb * p.n_tiles + n0 / BN;
         if (key != cur_key) {
           if (cur_key >= 0) flush();
@@ -248,31 +261,29 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN * Cfg::NSUB);
-      const int nsub_used = (p.ntaps * chunks < Cfg::NSUB) ? p.ntaps * chunks : Cfg::NSUB;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += CH) {
         float v[CH];
-        if constexpr (CH == 32) {
+        if constexpr (CH == 32)
           tmem_ld_32x32(taddr + c0, v);
-          tmem_ld_wait();
-        } else {
+        else
           tmem_ld_32x16(taddr + c0, v);
-          tmem_ld_wait();
-          for (int sub = 1; sub < nsub_used; ++sub) {
-            float u[CH];
-            tmem_ld_32x16(taddr + sub * BN + c0, u);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] += u[j];
-          }
-        }
+        tmem_ld_wait();
         const int cg = n0 + c0;
         if (cg >= p.cout_valid) break;
+        if (p.splitk > 1) {  // partial tile: fp32 vector atomics into the workspace (same NDHWC indexing as the output)
+          if (valid) {
+            float4* wsp = reinterpret_cast<float4*>(p.ws + roff + cg);
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) atomicAdd(wsp + j / 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + cg + j);
         if constexpr (CH == 32) {
-          if (p.stats) {
+          if (p.stats && p.splitk == 1) {
             const int gl = cg / p.cpg - cur_g0;
             if (p.cpg >= 32) chunk_stats<32>(v, valid, sstat, gl, lane);
             else if (p.cpg == 16) chunk_stats<16>(v, valid, sstat, gl, lane);
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (p.stats && cur_key >= 0) flush();
+    if (p.stats && p.splitk == 1 && cur_key >= 0) flush();
   }
 
   tc_fence_before();

@@ -23,6 +23,8 @@ struct ConvParams {
   int src_chunks0, src_chunks1;
   int W, H, D;            // logical grid of output positions per sample and class
   int groups, cpg, cout_valid, out_mode, act;
+  int splitk;             // k-splits per output tile (1 = off)
+  float* ws;              // split-K fp32 workspace, NDHWC like the output
 };
 
 }  // namespace b2v

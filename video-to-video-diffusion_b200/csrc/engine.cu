@@ -233,21 +233,30 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
       return out;
     }
   }
+  // split-K workspace: persistent and zero between uses (the finalize pass re-zeroes it), so not from the pool
+  const size_t sk_bytes = (!out_fp32 && ds) ? conv_splitk_ws_bytes(L, B, in0.D, in0.H, in0.W) : 0;
+  if (sk_bytes > sk_cap) {
+    sk_ws = (float*)ds->alloc(sk_bytes);
+    sk_cap = sk_ws ? sk_bytes : 0;
+  }
   const int rc = conv_plan(P, L, in0.p, in1 ? in1->p : nullptr, B, in0.D, in0.H, in0.W,
                            out_fp32 ? (void*)out_fp32 : (void*)out.p, out_fp32 ? OUT_F32 : OUT_CL16, stats, groups, act,
-                           err, ws);
+                           err, ws, (sk_bytes && sk_ws) ? sk_ws : nullptr);
   if (ws) pool.put(ws);
   if (rc) {
     fail(name + ": " + err);
     ok = false;
     return out;
   }
-  if (bias_override) P.p.bias = bias_override;
+  if (bias_override) {
+    P.p.bias = bias_override;
+    P.fin.bias = bias_override;
+  }
   Op op;
   op.name = name;
   op.flops = P.flops;
   op.bytes = 0;
-  op.launches = P.tapgemm ? 2 : 1;
+  op.launches = (P.tapgemm || P.splitk > 1) ? 2 : 1;
   op.out = out_fp32 ? (void*)out_fp32 : (void*)out.p;
   op.out_bytes = out_fp32 ? (size_t)B * L.cout * oD * oH * oW * 4 : (size_t)B * oD * oH * oW * L.cout * 2;
   op.run = [P](cudaStream_t st) { conv_launch(P, st); };

@@ -111,6 +111,9 @@ struct Builder {
   size_t stats_cap, stats_used = 0;
   bool ok = true;
   const TembSource* temb_src = nullptr;  // U-Net programs only
+  DeviceStore* ds = nullptr;             // owner of the zero-initialised split-K workspace
+  float* sk_ws = nullptr;
+  size_t sk_cap = 0;
   Builder(std::vector<Op>& o, Pool& p, int b, float* sb, size_t sc) : ops(o), pool(p), B(b), stats_base(sb), stats_cap(sc) {}
   Act alloc(int C, int D, int H, int W);
   void free(Act& a);

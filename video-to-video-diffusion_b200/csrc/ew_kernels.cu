@@ -206,6 +206,68 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
 #undef GN_LAUNCH
 }
 
+// Split-K epilogue (see conv_igemm.cuh): y = fp16(ws + bias), per-(sample, group) statistics of the fp32 sums, and the
+// workspace is handed back zeroed for the next split-K convolution of the program.
+__global__ void splitk_finalize_kernel(float* ws_, const float* __restrict__ bias, __half* out_, float* stats,
+                                       long long S, int C, int G) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int C8 = C >> 3, R = blockDim.x / C8, cv = threadIdx.x % C8, rr = threadIdx.x / C8, b = blockIdx.y;
+  float4* ws = reinterpret_cast<float4*>(ws_ + (size_t)b * S * C);
+  uint4* out = reinterpret_cast<uint4*>(out_ + (size_t)b * S * C);
+  float bs[8], as[8], ass[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bs[j] = bias[cv * 8 + j];
+    as[j] = ass[j] = 0.f;
+  }
+  for (long long row = (long long)blockIdx.x * R + rr; row < S; row += (long long)gridDim.x * R) {
+    const size_t idx = (size_t)row * C8 + cv;
+    const float4 a0 = ws[idx * 2], a1 = ws[idx * 2 + 1];
+    ws[idx * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ws[idx * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[8] = {a0.x + bs[0], a0.y + bs[1], a0.z + bs[2], a0.w + bs[3],
+                  a1.x + bs[4], a1.y + bs[5], a1.z + bs[6], a1.w + bs[7]};
+    out[idx] = f_to_h8(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      as[j] += f[j];
+      ass[j] += f[j] * f[j];
+    }
+  }
+  if (!stats) return;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[cv * 8 + j], as[j]);
+    atomicAdd(&sm[C + cv * 8 + j], ass[j]);
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      s += sm[g * cpg + j];
+      ss += sm[C + g * cpg + j];
+    }
+    atomicAdd(&stats[((size_t)b * G + g) * 2], s);
+    atomicAdd(&stats[((size_t)b * G + g) * 2 + 1], ss);
+  }
+}
+void launch_splitk_finalize(float* ws, const float* bias, __half* out, float* stats, int B, long long S, int C, int G,
+                            cudaStream_t st) {
+  const int C8 = C / 8;
+  const int R = C8 >= 256 ? 1 : 256 / C8;
+  long long want = (S + R - 1) / R;
+  long long cap = (148LL * 4 + B - 1) / B;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  launch_k(splitk_finalize_kernel, dim3(blocks, B), dim3(C8 * R), 2 * C * sizeof(float), st, ws, bias, out, stats, S, C,
+           G);
+}
+
 // Stand-alone statistics pass (used when the producer is not one of our conv / apply kernels, and by tests).
 __global__ void gn_stats_kernel(const __half* __restrict__ x_, long long S, int C, int G, float* stats) {
   pdl_trigger();

@@ -8,6 +8,8 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
                      const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
                      float eps, int mode, float* stats_out, int G_out, cudaStream_t st,
                      const int* temb_step = nullptr, long long temb_step_stride = 0);
+void launch_splitk_finalize(float* ws, const float* bias, __half* out, float* stats, int B, long long S, int C, int G,
+                            cudaStream_t st);
 void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st);
 void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
                       int T, int P, int C, int G, float eps, cudaStream_t st);

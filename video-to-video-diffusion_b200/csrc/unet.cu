@@ -175,7 +175,10 @@ struct UBuild {
   UNet& u;
   UProgram& up;
   Builder b;
-  UBuild(UNet& u_, UProgram& p) : u(u_), up(p), b(p.core, p.pool, p.B, p.stats, p.stats_cap) { b.temb_src = &p.temb; }
+  UBuild(UNet& u_, UProgram& p) : u(u_), up(p), b(p.core, p.pool, p.B, p.stats, p.stats_cap) {
+    b.temb_src = &p.temb;
+    b.ds = &p.ds;
+  }
 
   // ResBlock3D.forward (models/unet3d.py:116-133)
   Act res(const std::string& name, const ResW& r, const Act& x, const Act* skip, float** out_stats, int G_out) {

@@ -91,7 +91,7 @@ VAE::~VAE() {
 
 struct VBuild {
   Builder b;
-  VBuild(VProgram& p) : b(p.prog.ops, p.pool, p.B, p.stats, p.stats_cap) {}
+  VBuild(VProgram& p) : b(p.prog.ops, p.pool, p.B, p.stats, p.stats_cap) { b.ds = &p.ds; }
   // conv -> GN(8) -> SiLU ; consumes x
   Act block(const std::string& name, const VBlockW& w, Act& x) {
     float* s = b.new_stats(8);
