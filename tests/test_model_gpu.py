@@ -298,3 +298,39 @@ def test_config3_full_512_volume(cuda_dev, bench_model):
     p_new, p_ref = R.psnr(n(out), n(target)), R.psnr(n(ref), n(target))
     print(f"512^2 generate: PSNR(new,target)={p_new:.4f} PSNR(ref,target)={p_ref:.4f} PSNR(new,ref)={R.psnr(n(out), n(ref)):.2f}")
     assert abs(p_new - p_ref) <= 0.05
+
+
+def test_ragged_shapes_empty_batch_and_nan_input(cuda_dev):
+    """edge cases: odd depth / non-square latent (partial TMA boxes everywhere), batch 3, empty batch, NaNs in v_in"""
+    from v2v_b200.models import VideoToVideoDiffusion
+    g = golden("generate_tiny.pt")
+    torch.manual_seed(g["seed"])
+    m = VideoToVideoDiffusion(g["config"]).eval().to(cuda_dev)
+    sd = _sd(m, cuda_dev)
+    _, unet_cfg, _ = R.resolve_config(g["config"])
+    usd = {k[5:]: w for k, w in sd.items() if k.startswith("unet.")}
+    gen = torch.Generator().manual_seed(77)
+    for shape in [(3, 4, 5, 6, 10), (1, 4, 1, 2, 2), (2, 4, 7, 14, 6)]:
+        x = torch.randn(shape, generator=gen).to(cuda_dev)
+        c = torch.randn(shape, generator=gen).to(cuda_dev)
+        t = torch.randint(0, 1000, (shape[0],), generator=gen).to(cuda_dev)
+        with torch.no_grad():
+            ref = R.unet_forward(usd, unet_cfg, x, t, c)
+        assert rel_l2(m.unet(x, t, c), ref) < EPS_TOL, shape
+    vsd = {k[4:]: w for k, w in sd.items() if k.startswith("vae.")}
+    v = (torch.rand((2, 1, 3, 20, 28), generator=gen) * 2 - 1).to(cuda_dev)
+    with torch.no_grad():
+        zr = R.vae_encode(vsd, v, 0.5)
+        rr = R.vae_decode(vsd, zr, 0.5)
+    assert rel_l2(m.vae.encode(v), zr) < EPS_TOL and rel_l2(m.vae.decode(zr), rr) < EPS_TOL
+    # empty batch
+    e = torch.empty((0, 4, 4, 8, 8), device=cuda_dev)
+    assert m.unet(e, torch.empty((0,), dtype=torch.long, device=cuda_dev), e).shape == (0, 4, 4, 8, 8)
+    assert m.vae.decode(e).shape == (0, 1, 4, 32, 32)
+    assert m.generate(torch.empty((0, 1, 2, 16, 16), device=cuda_dev), "ddim", 2, target_depth=6).shape == (0, 1, 6, 16, 16)
+    # NaNs in the input are zeroed like the reference does (models/model.py:262-264)
+    vin = g["v_in"].to(cuda_dev).clone()
+    vin[0, 0, 0, 0, :4] = float("nan")
+    torch.manual_seed(1)
+    out = m.generate(vin, "ddim", 2, target_depth=6)
+    assert torch.isfinite(out).all()

@@ -99,6 +99,8 @@ class DDIMSampler(_Stitching):
         if not _is_native(self.model):
             return self._sample_generic(z, cond, ts, acp, eta)
         B, _, T, h, w = shape
+        if z.numel() == 0:
+            return z
         noise = None
         if eta > 0:  # the reference draws one randn_like per step; nothing else touches the RNG in between
             noise = torch.stack([torch.randn_like(z) for _ in range(n)]).contiguous()

@@ -87,6 +87,8 @@ class GaussianDiffusion(nn.Module):
         from .unet3d import UNet3D
         B = shape[0]
         z = torch.randn(shape, device=device)
+        if z.numel() == 0:
+            return z
         if not isinstance(model, UNet3D):
             for t_idx in reversed(range(self.timesteps)):
                 z = self.p_sample(model, z, torch.full((B,), t_idx, device=device, dtype=torch.long), c)

@@ -75,6 +75,9 @@ class VideoToVideoDiffusion(nn.Module):
         if sampler not in ("ddpm", "ddim"):
             raise ValueError(f"Unknown sampler: {sampler}")
         device = v_in.device
+        if v_in.numel() == 0:  # empty batch
+            B, C, T_in, H, W = v_in.shape
+            return torch.empty((B, C, target_depth or T_in, H, W), dtype=torch.float32, device=device)
         v_in = torch.nan_to_num(v_in.float(), nan=0.0, posinf=float("inf"), neginf=float("-inf"))
         z_in = _guard(self.vae.encode(v_in))
         if target_depth is not None:

@@ -140,6 +140,8 @@ class UNet3D(nn.Module):
         if c.shape != x.shape or t.shape != (B,) or L != self.latent_dim:
             raise ValueError(f"UNet3D.forward: x {tuple(x.shape)}, c {tuple(c.shape)}, t {tuple(t.shape)}")
         out = torch.empty_like(x)
+        if x.numel() == 0:  # empty batch: nothing to launch
+            return out
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().b2v_unet_forward(self.native(x.device), _lib.dptr(x), _lib.dptr(t, torch.int64),
                                                    _lib.dptr(c), _lib.dptr(out), B, T, h, w, _lib.stream()),

@@ -102,6 +102,8 @@ class SliceInterpolationVAE(nn.Module):
         if C != self.in_channels:
             raise ValueError(f"VAE.encode: expected {self.in_channels} channels, got {C}")
         z = torch.empty((B, self.latent_dim, T, H // 4, W // 4), dtype=torch.float32, device=x.device)
+        if z.numel() == 0:
+            return z
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().b2v_vae_encode(self.native(x.device), _lib.dptr(x), _lib.dptr(z), B, T, H, W,
                                                  _lib.stream()), "vae_encode")
@@ -114,6 +116,8 @@ class SliceInterpolationVAE(nn.Module):
         if L != self.latent_dim:
             raise ValueError(f"VAE.decode: expected {self.latent_dim} latent channels, got {L}")
         x = torch.empty((B, self.in_channels, T, 4 * h, 4 * w), dtype=torch.float32, device=z.device)
+        if x.numel() == 0:
+            return x
         with torch.cuda.device(z.device):
             _lib.check(_lib.lib().b2v_vae_decode(self.native(z.device), _lib.dptr(z), _lib.dptr(x), B, T, h, w,
                                                  _lib.stream()), "vae_decode")

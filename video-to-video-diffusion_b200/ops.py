@@ -96,6 +96,8 @@ def upsample_depth(z, depth):
     """F.interpolate(z, (depth, h, w), mode='trilinear', align_corners=False) for unchanged h, w"""
     B, C, D, H, W = z.shape
     out = torch.empty((B, C, depth, H, W), dtype=torch.float32, device=z.device)
+    if out.numel() == 0:
+        return out
     _lib.check(_lib.lib().b2v_upsample_depth(_lib.dptr(z.contiguous()), _lib.dptr(out), B * C, D, depth, H * W,
                                              _lib.stream()), "upsample_depth")
     return out
