@@ -44,6 +44,14 @@ CONV_CASES = [
     ("k3_dual_splitk", 0, 256, 256, 256, 1, 4, 6, 6),
     ("down_splitk", 2, 128, 0, 256, 1, 4, 12, 12),
     ("k3_splitk_b2", 0, 256, 0, 512, 2, 12, 6, 6),
+    # >= 75 output tiles with Cout % 256 == 0: the CTA-pair kernel (cta_group::2, two m-tiles per cluster);
+    # 27 x 3 m-tiles is an odd count (the last pair has a padding half) and pairs straddle samples
+    ("k3_pair_odd", 0, 64, 0, 256, 27, 5, 8, 8),
+    ("k3_pair_512", 0, 128, 0, 512, 10, 8, 8, 8),
+    ("k3_pair_dual", 0, 64, 64, 256, 20, 8, 8, 8),
+    ("k1_pair", 1, 128, 0, 256, 20, 8, 8, 8),
+    ("down_pair", 2, 64, 0, 256, 20, 8, 16, 16),
+    ("upT_pair", 3, 64, 0, 256, 5, 8, 8, 8),
 ]
 
 
@@ -132,6 +140,51 @@ def test_gn_apply_vs_torch(cuda_dev, C, G, mode):
     rg = got.reshape(B, Gout, -1)
     ref_so = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1)
     ok, msg = _report("gn.stats_out", so, ref_so, 1e-3)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("C,T,H,W,B", [(256, 12, 6, 6, 2), (512, 8, 3, 3, 1), (128, 5, 5, 7, 2), (64, 48, 4, 4, 1)])
+def test_fused_res_tail_plus_temporal_attention(cuda_dev, C, T, H, W, B):
+    """gn_res_tsum + attn_proj_add against the literal reference block (models/unet3d.py:126-133 ResBlock tail,
+    :163-194 TemporalAttention with its 'bhqk,bhvc->bhqc' einsum) in torch fp32."""
+    from v2v_b200 import ops
+    from einops import rearrange
+    g = torch.Generator().manual_seed(C + T)
+    heads = 4
+    y = torch.randn((B, C, T, H, W), generator=g).to(cuda_dev)
+    res = torch.randn((B, C, T, H, W), generator=g).to(cuda_dev)
+    gn2 = torch.nn.GroupNorm(32, C).to(cuda_dev)
+    gna = torch.nn.GroupNorm(32, C).to(cuda_dev)
+    qkv = torch.nn.Conv3d(C, 3 * C, 1).to(cuda_dev)
+    proj = torch.nn.Conv3d(C, C, 1).to(cuda_dev)
+    with torch.no_grad():
+        for m in (gn2, gna):
+            m.weight.copy_(1 + 0.2 * torch.randn(C, generator=g))
+            m.bias.copy_(0.2 * torch.randn(C, generator=g))
+        yh, rh = _h(y), _h(res)
+        h = F.silu(gn2(yh) + rh)
+        hq = _h(h)  # the kernel stores fp16 and the attention reads that
+        # literal TemporalAttention.forward
+        n = gna(hq)
+        q, k, v = qkv(n).chunk(3, dim=1)
+        q = rearrange(q, "b (h c) t x y -> (b x y) h t c", h=heads)
+        k = rearrange(k, "b (h c) t x y -> (b x y) h t c", h=heads)
+        v = rearrange(v, "b (h c) t x y -> (b x y) h t c", h=heads)
+        attn = torch.softmax(torch.einsum("bhqc,bhkc->bhqk", q, k) * (C // heads) ** -0.5, dim=-1)
+        o = torch.einsum("bhqk,bhvc->bhqc", attn, v)
+        o = rearrange(o, "(b x y) h t c -> b (h c) t x y", x=H, y=W)
+        ref = hq + proj(o)
+        Wv = qkv.weight[2 * C:, :, 0, 0, 0].double()
+        bv = qkv.bias[2 * C:].double()
+        Wp = proj.weight[:, :, 0, 0, 0].double()
+        wpv = (Wp @ Wv).float()
+        bias = (T * (Wp @ bv) + proj.bias.double()).float()
+    y16 = ops.to_cl16(y)
+    st_in = ops.gn_stats(y16, 32)
+    out = ops.res_attn_tail(y16, ops.to_cl16(res), st_in, gn2.weight.detach(), gn2.bias.detach(), 32,
+                            gna.weight.detach(), gna.bias.detach(), 32, wpv.contiguous(), bias.contiguous())
+    torch.cuda.synchronize()
+    ok, msg = _report(f"res_attn_tail C{C}", ops.from_cl16(out), ref, 4e-3)
     assert ok, msg
 
 

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b2v_nc32_to_cl16": (c_int, [_P, _P, c_int, c_int, c_int, c_longlong, _P]),
     "b2v_cl16_to_nc32": (c_int, [_P, _P, c_int, c_int, c_int, c_longlong, _P]),
     "b2v_gn_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, c_int, _P, c_int, _P]),
+    "b2v_res_attn_tail": (c_int, [_P, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, _P, c_longlong, c_int, c_int,
+                                  c_int, c_int, _P]),
     "b2v_gn_stats": (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, _P]),
     "b2v_ddim_update": (c_int, [_P, _P, _P, _P, c_longlong, _P, _P]),
 }

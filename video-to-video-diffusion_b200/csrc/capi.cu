@@ -273,6 +273,23 @@ int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* g
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
+int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const float* gamma2, const float* beta2, int G2,
+                      const float* gamma_a, const float* beta_a, int Ga, const void* wt, const float* bias,
+                      float* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream) {
+  if (!attn_fused_supported(C)) return fail("res_attn_tail: unsupported channel count for the fused attention path");
+  static const int setup = attn_setup_kernels();
+  if (setup) return fail("res_attn_tail: cudaFuncSetAttribute failed");
+  const int TS = attn_tsum_splits(B, T, P, C);
+  if ((long long)B * TS * P * C > tsum_cap) return fail("res_attn_tail: depth-sum workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_gn_res_tsum((__half*)y, (const __half*)res, stats_in, gamma2, beta2, B, T, P, C, G2, 1e-5f, stats_mid, Ga,
+                     tsum_ws, TS, st);
+  launch_attn_proj_add((__half*)y, tsum_ws, TS, stats_mid, gamma_a, beta_a, (const __half*)wt, bias, B, T, P, C, Ga,
+                       1e-5f, st);
+  g_launches += 2;
+  B2V_CUDA(cudaGetLastError());
+  return 0;
+}
 int b2v_gn_stats(const void* x, int B, long long S, int C, int G, float* stats, void* stream) {
   launch_gn_stats((const __half*)x, B, S, C, G, stats, (cudaStream_t)stream);
   g_launches += 1;

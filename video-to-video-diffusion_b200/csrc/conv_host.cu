@@ -76,6 +76,8 @@ static inline __half to_operand(float x) {
   return __float2half_rn(x);
 }
 
+__half conv_operand(float x) { return to_operand(x); }
+
 int conv_setup_kernels(std::string& err) {
   cudaError_t e;
   {
@@ -91,11 +93,18 @@ int conv_setup_kernels(std::string& err) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<256>::SMEM);
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ConvCfg<256, true>::SMEM);
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_igemm_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfgT::SMEM);
   if (e != cudaSuccess) {
     err = std::string("cudaFuncSetAttribute(conv_igemm): ") + cudaGetErrorString(e);
+    return -1;
+  }
+  if (attn_setup_kernels()) {
+    err = "cudaFuncSetAttribute(attn_proj_add) failed";
     return -1;
   }
   return 0;
@@ -224,19 +233,22 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * L.cout_pad * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)L.bn, 1};
   if (encode_map(&L.tmB, L.w, 3, dims, strides, box, err)) return -1;
+  cuuint32_t box2[3] = {64, (cuuint32_t)(L.bn >= 32 ? L.bn / 2 : L.bn), 1};
+  if (encode_map(&L.tmB2, L.w, 3, dims, strides, box2, err)) return -1;
   if (kind == CONV_K3 && cout <= 16 && cin1 == 0) {
-    // tap-GEMM layout: row (tap*Cout + co) holds w[co][:, tap]
-    L.tap_row_tiles = (27 * cout + 127) / 128;
+    // tap-GEMM layout: [kd][row][cin], row (kh*3+kw)*Cout + co holds w[co][:, kd, kh, kw] -- the depth taps are
+    // accumulated inside the GEMM (three depth-shifted loads), the 3x3 in-plane taps stay separate rows
+    L.tap_row_tiles = (9 * cout + 127) / 128;
     const int rows = L.tap_row_tiles * 128;
-    std::vector<__half> wg((size_t)rows * cin, __float2half(0.f));
+    std::vector<__half> wg((size_t)3 * rows * cin, __float2half(0.f));
     for (int t = 0; t < 27; ++t)
       for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci)
         {
-          // logical row r = t*cout + co lives in UMMA row (r % 4) * 32 + r / 4 of its 128-row tile (see MODE 1 epilogue)
-          const int r = t * cout + co, tile = r / 128, rl = r % 128;
+          // logical row r lives in UMMA row (r % 4) * 32 + r / 4 of its 128-row tile (see MODE 1 epilogue)
+          const int kd = t / 9, r = (t % 9) * cout + co, tile = r / 128, rl = r % 128;
           const int phys = tile * 128 + (rl % 4) * 32 + rl / 4;
-          wg[(size_t)phys * cin + ci] = to_operand(wc(co, ci, t / 9, (t / 3) % 3, t % 3));
+          wg[((size_t)kd * rows + phys) * cin + ci] = to_operand(wc(co, ci, kd, (t / 3) % 3, t % 3));
         }
     e = cudaMalloc(&L.wg, wg.size() * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemcpy(L.wg, wg.data(), wg.size() * sizeof(__half), cudaMemcpyHostToDevice);
@@ -244,7 +256,7 @@ int conv_layer_init(ConvLayer& L, int kind, const float* w, const float* b, int 
       err = std::string("conv tap-gemm weights upload: ") + cudaGetErrorString(e);
       return -1;
     }
-    cuuint64_t gd[3] = {(cuuint64_t)cin, (cuuint64_t)rows, 1};
+    cuuint64_t gd[3] = {(cuuint64_t)cin, (cuuint64_t)rows, 3};
     cuuint64_t gs[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * rows * 2};
     cuuint32_t gb[3] = {64, 128, 1};
     if (encode_map(&L.tmBg, L.wg, 3, gd, gs, gb, err)) return -1;
@@ -310,43 +322,49 @@ size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
   return (size_t)N * gD * gH * gW * L.cout * sizeof(float);
 }
 
-static inline long long tap_pairs(long long positions) { return ((positions + 127) / 128 + 1) / 2; }
+// tap-GEMM position tiles: 128 consecutive (h, w) positions of one depth slice; slices are padded to whole tiles
+static inline long long tap_slice_tiles(int H, int W) { return ((long long)H * W + 127) / 128; }
+static inline long long tap_pairs(int N, int D, int H, int W) { return (tap_slice_tiles(H, W) * D * N + 1) / 2; }
 
 size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
   static const bool off = getenv("B2V_NO_TAPGEMM") != nullptr;
   if (!L.tapgemm || off) return 0;
-  return (size_t)27 * L.cout * (size_t)(tap_pairs((long long)N * D * H * W) * 256) * sizeof(float);
+  return (size_t)9 * L.cout * (size_t)(tap_pairs(N, D, H, W) * 256) * sizeof(float);
 }
 
-// GEMM over the flattened volume: P[(tap,co)][position] = sum_c w[co][c][tap] * x[position][c]
+// GEMM over depth-slice tiles: P[(kh,kw,co)][n,d,hw] = sum_kd sum_c w[co][c][kd,kh,kw] * x[n][d+kd-1][hw][c]
+// (out-of-range depths are zero-filled by TMA = the conv padding along d)
 static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int N, int D, int H, int W, void* out,
                         int act, std::string& err, float* ws) {
   ConvParams& p = P.p;
   p.splitk = 1;
   const long long pos = (long long)N * D * H * W;
-  const long long pairs = tap_pairs(pos);
+  const long long hw = (long long)H * W;
+  const long long pairs = tap_pairs(N, D, H, W);
   p.bw = 128;
   p.bh = p.bd = 1;
   p.rows_valid = 128;
-  p.tiles_w = (int)((pos + 127) / 128);
-  p.tiles_h = p.tiles_d = 1;
-  p.batch = 1;
+  p.tiles_w = (int)tap_slice_tiles(H, W);
+  p.tiles_h = 1;
+  p.tiles_d = D;
+  p.batch = N;
   p.n_tiles = L.tap_row_tiles;
   p.nclass = 1;
-  p.ntaps = 1;
+  p.ntaps = 3;
   p.src_chunks0 = L.cin0_pad / 64;
   p.src_chunks1 = 0;
-  p.taps[0] = enc_tap(0, 0, 0, 0);
+  for (int kd = 0; kd < 3; ++kd) p.taps[kd] = enc_tap(0, kd - 1, 0, 0);
   p.tmB = L.tmBg;
-  p.W = (int)pos;
-  p.H = p.D = 1;
+  p.W = (int)hw;
+  p.H = 1;
+  p.D = D;
   p.cpg = 1;
-  p.cout_valid = 27 * L.cout;
+  p.cout_valid = 9 * L.cout;
   p.out = ws;
   p.sC = pairs * 256;
   const cuuint64_t C = L.cin0_pad;
-  cuuint64_t dims[5] = {C, (cuuint64_t)pos, 1, 1, 1};
-  cuuint64_t st[4] = {C * 2, (cuuint64_t)pos * C * 2, (cuuint64_t)pos * C * 2, (cuuint64_t)pos * C * 2};
+  cuuint64_t dims[5] = {C, (cuuint64_t)hw, 1, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t st[4] = {C * 2, (cuuint64_t)hw * C * 2, (cuuint64_t)hw * C * 2, (cuuint64_t)D * hw * C * 2};
   cuuint32_t box[5] = {64, 128, 1, 1, 1};
   if (encode_map(&p.tmA[0], in0, 5, dims, st, box, err)) return -1;
   P.tapgemm = true;
@@ -360,6 +378,7 @@ static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int 
   P.st.W = W;
   P.st.act = act;
   P.st.row_stride = pairs * 256;
+  P.st.slice_stride = tap_slice_tiles(H, W) * 128;
   const long long total = pairs * L.tap_row_tiles;
   const int sms = device_sm_count();
   P.grid = (int)(total < sms ? total : sms);
@@ -410,6 +429,7 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
   p.src_chunks1 = L.cin1_pad / 64;
   memcpy(p.taps, L.taps, sizeof(p.taps));
   p.tmB = L.tmB;
+  p.tmB2 = L.tmB2;
   p.bias = L.bias;
   p.stats = stats;
   p.groups = groups;
@@ -491,7 +511,17 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
       P.fin.B = N;
     }
   }
-  P.grid = (int)(total < sms ? total : sms);
+  // CTA pairs (cta_group::2) for the wide layers: a work unit is two consecutive m-tiles of one (class, n-tile)
+  static const bool no_pair = getenv("B2V_NO_PAIR") != nullptr;
+  P.pair = !no_pair && !P.swapped && P.splitk == 1 && L.bn == 256 && sms >= 2;
+  if (P.pair) {
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N;
+    total = ((m_tiles + 1) / 2) * p.nclass * p.n_tiles;
+    const long long clusters = total < sms / 2 ? total : sms / 2;
+    P.grid = (int)(2 * clusters);
+  } else {
+    P.grid = (int)(total < sms ? total : sms);
+  }
   const double taps_real = (L.kind == CONV_K1) ? 1 : (L.kind == CONV_DOWN || L.kind == CONV_UPT) ? 48 : 27;
   const double pos = (L.kind == CONV_UPT) ? (double)N * D * H * W : (double)N * gD * gH * gW;
   P.flops = 2.0 * pos * taps_real * (double)(L.cin0 + L.cin1) * (double)L.cout;
@@ -503,7 +533,7 @@ void conv_launch(const ConvPlan& P, cudaStream_t st) {
     static const int dbg = getenv("B2V_TAP_DEBUG") ? atoi(getenv("B2V_TAP_DEBUG")) : 0;  // 1: GEMM only, 2: stencil only
     if (dbg != 2) launch_k(conv_igemm_t_kernel<1>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
     if (dbg != 1) launch_head_stencil(P.st.P, P.st.bias, P.st.out, P.st.N, P.st.cout, P.st.D, P.st.H, P.st.W, P.st.row_stride,
-                        P.st.act, st);
+                        P.st.slice_stride, P.st.act, st);
     return;
   }
   if (P.swapped) {
@@ -517,6 +547,10 @@ void conv_launch(const ConvPlan& P, cudaStream_t st) {
       default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
     }
     launch_splitk_finalize(P.fin.ws, P.fin.bias, P.fin.out, P.fin.stats, P.fin.B, P.fin.S, P.fin.C, P.fin.G, st);
+    return;
+  }
+  if (P.pair) {
+    launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(192), ConvCfg<256, true>::SMEM, st, P.p);
     return;
   }
   switch (P.bn) {

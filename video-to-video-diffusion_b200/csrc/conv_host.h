@@ -26,12 +26,12 @@ struct ConvLayer {
   int ntaps = 0, nclass = 1;
   __half* w = nullptr;   // device [nclass*ntaps][cout_pad][cin0_pad+cin1_pad]
   float* bias = nullptr; // device [cout_pad]
-  CUtensorMap tmB;
+  CUtensorMap tmB, tmB2;  // full-tile / half-tile (CTA pair) boxes
   int32_t taps[48];
   // narrow 3x3x3 heads (Cout <= 16, Cin % 64 == 0): second weight layout for the tap-GEMM path
   bool tapgemm = false;
-  int tap_row_tiles = 0;    // ceil(27*Cout / 128)
-  __half* wg = nullptr;     // device [tap_row_tiles*128][Cin]: row = tap*Cout + co
+  int tap_row_tiles = 0;    // ceil(9*Cout / 128)
+  __half* wg = nullptr;     // device [kd][tap_row_tiles*128][Cin]: row = (kh*3+kw)*Cout + co
   CUtensorMap tmBg;
 };
 
@@ -40,6 +40,7 @@ struct ConvPlan {
   int bn = 0;
   int grid = 0;
   bool swapped = false;  // Cout == 128: operand-swapped kernel (conv_igemm_t.cuh)
+  bool pair = false;     // BN == 256: CTA-pair kernel (cta_group::2, M = 256 per cluster)
   // tap-GEMM head: p describes the GEMM, the stencil pass below turns its rows into the NCDHW fp32 output
   bool tapgemm = false;
   struct {
@@ -47,7 +48,7 @@ struct ConvPlan {
     const float* bias;
     float* out;
     int N, cout, D, H, W, act;
-    long long row_stride;
+    long long row_stride, slice_stride;
   } st;
   // split-K (small-M layers): the conv kernel adds fp32 partial tiles into fin.ws, fin describes the finalize pass
   int splitk = 1;
@@ -80,5 +81,6 @@ size_t conv_tap_ws_bytes(const ConvLayer& L, int N, int D, int H, int W);
 void conv_launch(const ConvPlan& P, cudaStream_t st);
 int conv_setup_kernels(std::string& err);  // opt-in to large dynamic shared memory; call once per device
 int device_sm_count();
+__half conv_operand(float x);  // fp32 -> MMA operand (fp16; BF16-rounded first under B2V_OPERANDS=bf16)
 
 }  // namespace b2v

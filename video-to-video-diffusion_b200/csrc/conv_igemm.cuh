@@ -22,12 +22,15 @@
 
 namespace b2v {
 
-template <int BN>
+// PAIR: two CTAs of a (2,1,1) cluster run one M = 256 x N = BN MMA (tcgen05 cta_group::2): each CTA stages its own
+// 128-position A box and HALF of the weight tile, so the weight bytes moved L2 -> shared memory and read from shared
+// memory per FLOP are halved (the step is power-limited: operand movement is what is left to save).
+template <int BN, bool PAIR = false>
 struct ConvCfg {
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = PAIR ? BN * 64 : BN * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int NSTAGE = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*group stats*/;
 };
@@ -86,9 +89,9 @@ __device__ __forceinline__ int unit_k1(int unit, int ksteps, int S) {
   return (int)((long long)(unit % S + 1) * ksteps / S);
 }
 
-template <int BN>
+template <int BN, bool PAIR = false>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, PAIR>;
   constexpr int NSTAGE = Cfg::NSTAGE;
   constexpr int CH = (BN >= 32) ? 32 : 16;  // epilogue column chunk
 
@@ -104,10 +107,16 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // PAIR: a work unit is two consecutive m-tiles (one per CTA) of one (class, n-tile); both CTAs of a cluster walk
+  // the same unit sequence.  m_units = m-tiles (or m-tile pairs) per (class, n-tile).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
-  const int total_tiles = m_tiles * p.nclass * p.n_tiles;
+  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int total_tiles = m_units * p.nclass * p.n_tiles;
   const int total_units = total_tiles * p.splitk;
   const int chunks = p.src_chunks0 + p.src_chunks1;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -118,14 +127,18 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs release the leader's accumulator
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, Cfg::TM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TM_COLS);
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // prologue done (barriers, TMEM, descriptors): let the next kernel start its own, then wait for our producer
@@ -139,10 +152,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int ksteps = p.ntaps * chunks;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int tile = unit / p.splitk;
-        int m = tile % m_tiles;
-        int rest = tile / m_tiles;
+        int m = PAIR ? 2 * (tile % m_units) + (int)rank : tile % m_units;
+        int rest = tile / m_units;
         const int cls = rest % p.nclass;
         const int n0 = (rest / p.nclass) * BN;
         const int w0 = (m % p.tiles_w) * p.bw;
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         const int h0 = (m % p.tiles_h) * p.bh;
         m /= p.tiles_h;
         const int d0 = (m % p.tiles_d) * p.bd;
-        const int nb = m / p.tiles_d;
+        const int nb = m / p.tiles_d;  // == batch for the missing second tile of an odd count: TMA zero-fills it
         const int k0 = unit_k0(unit, ksteps, p.splitk), k1 = unit_k1(unit, ksteps, p.splitk);
         int t = k0 / chunks, c = k0 % chunks;
         for (int k = k0; k < k1; ++k) {
@@ -163,10 +176,18 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           const int src = (c >= p.src_chunks0) ? 1 : 0;
           const int cc = src ? (c - p.src_chunks0) : c;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE;
-          tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
-          tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
+          if constexpr (PAIR) {
+            // the leader's barrier counts the bytes of both CTAs; its own arrive.expect_tx is the one pending arrival
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (a_bytes + (uint32_t)Cfg::B_BYTES));
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            tma_load_5d_2sm(sa, &p.tmA[map + src], lbar, cc * 64, cw, chh, cd, nb);
+            tma_load_3d_2sm(sa + Cfg::A_BYTES, &p.tmB2, lbar, c * 64, n0 + (int)rank * (BN / 2), tg);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
+            tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
+            tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
+          }
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
@@ -179,14 +200,14 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN, 0);
+    // ------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 256 : 128, BN, 0);
       const int ksteps = p.ntaps * chunks;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -200,15 +221,21 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           const uint64_t adesc = umma_desc_sw128(sa);
           const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          for (int kk = 0; kk < 4; ++kk) {
+            if constexpr (PAIR)
+              umma_f16_2sm(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+            else
+              umma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+          }
+          if constexpr (PAIR) umma_commit_2sm(&empty[stage], 3);  // frees the stage in both CTAs
+          else umma_commit(&empty[stage]);
           if (++stage == NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (PAIR) umma_commit_2sm(&tfull[acc], 3);
+        else umma_commit(&tfull[acc]);
       }
     }
   } else {
@@ -233,12 +260,20 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
     int it = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+    const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
       const int tile = unit / p.splitk;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int m = tile % m_tiles;
-      int rest = tile / m_tiles;
+      int m = PAIR ? 2 * (tile % m_units) + (int)rank : tile % m_units;
+      if (PAIR && m >= m_tiles) {  // odd tile count: this CTA's half of the last pair is padding
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        continue;
+      }
+      int rest = tile / m_units;
       const int cls = rest % p.nclass;
       const int n0 = (rest / p.nclass) * BN;
       const int w = (m % p.tiles_w) * p.bw + rw;
@@ -322,14 +357,22 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tempty_leader + (uint32_t)acc * 8u);
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     if (p.stats && p.splitk == 1 && cur_key >= 0) flush();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TM_COLS);
+  if constexpr (PAIR) {
+    cluster_sync_all();  // both CTAs are done with the shared accumulator and with each other's barriers
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::TM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TM_COLS);
+  }
 }
 
 }  // namespace b2v

@@ -27,9 +27,11 @@ struct ConvCfgT {
 };
 
 // MODE 0: convolution (above).  MODE 1 ("tap GEMM", narrow heads Cout <= 16): the 128 "channel" rows are
-// (tap, cout) pairs of a 3x3x3 filter, the positions are the flattened volume with no halo, and the raw fp32
-// products P[tap*Cout+co][position] are stored row-wise; head_stencil_kernel then sums the 27 shifted rows.
-// The input is read ONCE instead of once per tap (the N=16 implicit GEMM was L2-bound at ~7 TB/s).
+// (kh, kw, cout) triples of a 3x3x3 filter, the positions are 128-wide runs of one depth slice with no in-plane halo,
+// the three depth taps are accumulated in the K loop (depth-shifted TMA loads, zero-filled outside the volume), and
+// the raw fp32 products P[(kh*3+kw)*Cout+co][position] are stored row-wise; head_stencil_kernel then sums the 9
+// in-plane shifted rows.  The input is read 3 times (L2 hits) instead of 27 (the N=16 implicit GEMM was L2-bound at
+// ~7 TB/s) and P is 9*Cout rows (a 27*Cout-row P with the input read once spilled the L2: 382 MB for the U-Net head).
 template <int MODE>
 __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfgT;

@@ -11,6 +11,7 @@ enum { ACT_NONE = 0, ACT_TANH = 1 };
 struct ConvParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmB2;       // weight map with a half-height box (BN/2 rows): CTA-pair kernels load half a tile each
   int32_t taps[48];       // per (class, tap): (map << 24) | ((dd+8) << 16) | ((dh+8) << 8) | (dw+8)
   long long cls_off[4];   // output element offset of each class
   long long sN, sD, sH, sW, sC;  // output strides (elements)

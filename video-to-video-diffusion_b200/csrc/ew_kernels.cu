@@ -408,6 +408,267 @@ void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused form of the attention-followed ResBlock tail + TemporalAttention (two launches instead of four, and the
+// block output is read once less):
+//   gn_res_tsum   : y = silu(GN(y) + res) in place (ResBlock3D tail, mode 1 of gn_apply), statistics of the result for
+//                   the attention's GroupNorm, and the raw depth sums  tsum[b][ts][p][c] = sum_{t in split ts} y[b,t,p,c]
+//                   -- a thread owns one (position, 8-channel vector) and walks the depth axis, so the depth sum is a
+//                   register accumulation and doubles as the thread's contribution to the group sums
+//   attn_proj_add : s = gamma*rstd*(sum_ts tsum - T*mean) + T*beta ;  g = Wpv*s + (T*u + bp) ;  x[b,t,p,:] += g[p,:]
+//                   one CTA per PB positions: s and g live in shared memory, the C x C product runs on the CUDA cores
+//                   (2*C*C FLOP per position: 0.3 GFLOP per block at level 1 -- launch latency of a tensor-core GEMM
+//                   kernel was 3x its math time), the broadcast add streams the T slices.
+// ------------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(256) gn_res_tsum_kernel(__half* y_, const __half* res_,
+                                                          const float* __restrict__ stats_in,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int T, int P, int C, int G, float eps, float* stats_out,
+                                                          int G_out, float* tsum) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];  // [2*C]
+  const int C8 = C >> 3;
+  const int PB = blockDim.x / C8;
+  const int cv = threadIdx.x % C8, pp = threadIdx.x / C8;
+  const int b = blockIdx.z, ts = blockIdx.y, TS = gridDim.y;
+  const int p = blockIdx.x * PB + pp;
+  const int t0 = (int)((long long)ts * T / TS), t1 = (int)((long long)(ts + 1) * T / TS);
+  const int cpg = C / G;
+  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
+  float sc[8], sh[8], acc[8], acc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float s = stats_in[((size_t)b * G + g) * 2];
+    const float ss = stats_in[((size_t)b * G + g) * 2 + 1];
+    const float mean = s * inv_n;
+    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+    const float ga = gamma[c];
+    sc[j] = ga * rstd;
+    sh[j] = beta[c] - mean * ga * rstd;
+    acc[j] = acc2[j] = 0.f;
+  }
+  if (p < P && pp < PB) {
+    const size_t tstride = (size_t)P * C8;
+    const size_t base = ((size_t)b * T * P + p) * C8 + cv;
+    uint4* y = reinterpret_cast<uint4*>(y_) + base;
+    const uint4* res = res_ ? reinterpret_cast<const uint4*>(res_) + base : nullptr;
+    for (int t = t0; t < t1; t += U) {
+      uint4 yv[U], rv[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (t + k < t1) {
+          yv[k] = y[(size_t)(t + k) * tstride];
+          if (res) rv[k] = res[(size_t)(t + k) * tstride];
+        }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (t + k >= t1) break;
+        float f[8], rf[8];
+        h8_to_f(yv[k], f);
+        if (res) {
+          h8_to_f(rv[k], rf);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rf[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j] * sc[j] + sh[j] + rf[j]);
+        const uint4 o = f_to_h8(f);
+        y[(size_t)(t + k) * tstride] = o;
+        h8_to_f(o, f);  // sums of the values the consumers will actually read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += f[j];
+          acc2[j] += f[j] * f[j];
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(tsum + (((size_t)b * TS + ts) * P + p) * C + cv * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  if (pp < PB) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[cv * 8 + j], acc[j]);
+      atomicAdd(&sm[C + cv * 8 + j], acc2[j]);
+    }
+  }
+  __syncthreads();
+  const int cpo = C / G_out;
+  for (int g = threadIdx.x; g < G_out; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int j = 0; j < cpo; ++j) {
+      s += sm[g * cpo + j];
+      ss += sm[C + g * cpo + j];
+    }
+    atomicAdd(&stats_out[((size_t)b * G_out + g) * 2], s);
+    atomicAdd(&stats_out[((size_t)b * G_out + g) * 2 + 1], ss);
+  }
+}
+
+// depth splits so that about two waves of CTAs cover (B, P): the small levels have too few positions otherwise
+int attn_tsum_splits(int B, int T, int P, int C) {
+  const int C8 = C / 8;
+  const int PB = 256 / C8 > 0 ? 256 / C8 : 1;
+  const long long blocks = (long long)B * ((P + PB - 1) / PB);
+  int TS = 1;
+  while (blocks * TS < 256 && TS * 2 <= T / 4) TS *= 2;
+  return TS;
+}
+
+void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, const float* gamma, const float* beta,
+                        int B, int T, int P, int C, int G, float eps, float* stats_out, int G_out, float* tsum, int TS,
+                        cudaStream_t st) {
+  const int C8 = C / 8;
+  const int PB = 256 / C8;
+  const dim3 grid((P + PB - 1) / PB, TS, B);
+  launch_k(gn_res_tsum_kernel<4>, grid, dim3(C8 * PB), 2 * C * sizeof(float), st, y, res, stats_in, gamma, beta, T, P,
+           C, G, eps, stats_out, G_out, tsum);
+}
+
+template <int PB>
+__global__ void __launch_bounds__(512) attn_proj_add_kernel(__half* x_, const float* __restrict__ tsum, int TS,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
+                                                            const float* __restrict__ bias, int T, int P, int C, int G,
+                                                            float eps) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];  // s[PB][C], g[PB][C], part[NCG][PB][C]
+  const int C8 = C >> 3;
+  const int NCG = blockDim.x / C8;  // k-splits of the C x C product
+  const int CK = C / NCG;
+  const int b = blockIdx.y, p0 = blockIdx.x * PB;
+  float* s = sm;
+  float* gs = sm + PB * C;
+  float* part = sm + 2 * PB * C;
+  const int cpg = C / G;
+  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
+  for (int i = threadIdx.x; i < PB * C; i += blockDim.x) {
+    const int pl = i / C, c = i % C, p = p0 + pl;
+    float v = 0.f;
+    if (p < P)
+      for (int ts = 0; ts < TS; ++ts) v += tsum[(((size_t)b * TS + ts) * P + p) * C + c];
+    const int g = c / cpg;
+    const float su = stats[((size_t)b * G + g) * 2], ss = stats[((size_t)b * G + g) * 2 + 1];
+    const float mean = su * inv_n;
+    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+    s[i] = gamma[c] * rstd * (v - (float)T * mean) + (float)T * beta[c];
+  }
+  __syncthreads();
+  {
+    // thread = (8 output channels, k-split): CK independent 16-byte weight loads (a warp reads whole 512-byte runs
+    // of one weight row), fp32 FMAs against the shared-memory s; partial sums meet in shared memory in a fixed order
+    const int cov = threadIdx.x % C8, cg = threadIdx.x / C8;
+    float acc[PB][8];
+#pragma unroll
+    for (int k = 0; k < PB; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    const uint4* w8 = reinterpret_cast<const uint4*>(Wt) + (size_t)cg * CK * C8 + cov;
+    const float* sp = s + cg * CK;
+#pragma unroll 8
+    for (int c = 0; c < CK; ++c) {
+      float w[8];
+      h8_to_f(w8[(size_t)c * C8], w);
+#pragma unroll
+      for (int k = 0; k < PB; ++k) {
+        const float sv = sp[k * C + c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(w[j], sv, acc[k][j]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PB; ++k) {
+      float4* o = reinterpret_cast<float4*>(part + ((size_t)cg * PB + k) * C + cov * 8);
+      o[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      o[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PB * C; i += blockDim.x) {
+    float a = bias[i % C];
+    for (int cg = 0; cg < NCG; ++cg) a += part[(size_t)cg * PB * C + i];
+    gs[i] = a;
+  }
+  __syncthreads();
+  // x[b, t, p0 + pl, :] += g[pl, :]: rows (t, pl); for a fixed t the PB positions are one contiguous run
+  const int pbv = min(PB, P - p0);
+  const int cv = threadIdx.x % C8, r0 = threadIdx.x / C8, RPI = blockDim.x / C8;
+  const int rows = T * pbv;
+  uint4* x = reinterpret_cast<uint4*>(x_) + ((size_t)b * T * P + p0) * C8 + cv;
+  constexpr int U = 4;
+  for (int r = r0; r < rows; r += U * RPI) {
+    uint4 xv[U];
+    size_t off[U];
+    int pl[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int rr = r + k * RPI;
+      if (rr < rows) {
+        const int t = rr / pbv;
+        pl[k] = rr - t * pbv;
+        off[k] = ((size_t)t * P + pl[k]) * C8;
+        xv[k] = x[off[k]];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (r + k * RPI >= rows) break;
+      float f[8];
+      h8_to_f(xv[k], f);
+      const float4 g0 = *reinterpret_cast<const float4*>(gs + pl[k] * C + cv * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gs + pl[k] * C + cv * 8 + 4);
+      f[0] += g0.x; f[1] += g0.y; f[2] += g0.z; f[3] += g0.w;
+      f[4] += g1.x; f[5] += g1.y; f[6] += g1.z; f[7] += g1.w;
+      x[off[k]] = f_to_h8(f);
+    }
+  }
+}
+
+// 512 threads = C/8 channel vectors x 512/(C/8) k-splits, so C must be a multiple of 64 (and C/8 <= 256)
+bool attn_fused_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 2048 && 256 % (C / 8) == 0; }
+
+static size_t attn_proj_add_smem(int PB, int C) {
+  return (size_t)(2 * PB * C + (512 / (C / 8)) * PB * C) * sizeof(float);
+}
+
+int attn_setup_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(attn_proj_add_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attn_proj_add_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attn_proj_add_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  return e == cudaSuccess ? 0 : -1;
+}
+
+void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* stats, const float* gamma,
+                          const float* beta, const __half* Wt, const float* bias, int B, int T, int P, int C, int G,
+                          float eps, cudaStream_t st) {
+  // positions per CTA: the most (<= 4, fewer re-reads of the C x C weights) that still gives about one CTA per SM
+  int pb = 1;
+  for (int c = 2; c <= 4; c *= 2)
+    if ((long long)B * ((P + c - 1) / c) >= 140) pb = c;
+  const dim3 grid((P + pb - 1) / pb, B);
+  const size_t smem = attn_proj_add_smem(pb, C);
+#define APA(PP)                                                                                                       \
+  launch_k(attn_proj_add_kernel<PP>, grid, dim3(512), smem, st, x, tsum, TS, stats, gamma, beta, Wt, bias, T, P, C, G, \
+           eps)
+  if (pb == 4) APA(4);
+  else if (pb == 2) APA(2);
+  else APA(1);
+#undef APA
+}
+
+// ------------------------------------------------------------------------------------------------
 // Time embedding (reference models/unet3d.py:18-48 and the per-block time_mlp :88-91,123-125).
 //   temb_mlp : sinusoid(t) -> Linear(dim,td) -> SiLU -> Linear(td,td); stores SiLU(temb) (what every block consumes)
 //   temb_proj: all ResBlock projections at once: out[b][row] = W[row,:].silu_temb[b,:] + bias[row]
@@ -703,12 +964,14 @@ void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// Narrow 3x3x3 heads (Cout <= 16: U-Net conv_out, VAE encoder/decoder conv_out), second half: the tap GEMM wrote
-// P[(tap*Cout+co)][position]; out[n,co,d,h,w] = bias[co] + sum_tap P[tap*Cout+co][pos(n,d+dd,h+dh,w+dw)] over the
-// in-bounds taps (zero padding), optional tanh, fp32 NCDHW.  HBM-bound: every P element is read exactly once.
+// Narrow 3x3x3 heads (Cout <= 16: U-Net conv_out, VAE encoder/decoder conv_out), second half: the tap GEMM summed
+// the three depth taps and wrote P[(kh*3+kw)*Cout+co][n][d][hw (padded to slice_stride)];
+// out[n,co,d,h,w] = bias[co] + sum_{kh,kw} P[(kh*3+kw)*Cout+co][n,d,(h+kh-1)*W + w+kw-1] over the in-bounds taps
+// (zero padding), optional tanh, fp32 NCDHW.  Every P element is read exactly once.
 // ------------------------------------------------------------------------------------------------
 __global__ void head_stencil_kernel(const float* __restrict__ P, const float* __restrict__ bias, float* out,
-                                    int cout, int D, int H, int W, long long row_stride, int act, long long total) {
+                                    int cout, int D, int H, int W, long long row_stride, long long slice_stride,
+                                    int act, long long total) {
   pdl_trigger();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (n, co, d, h, w)
@@ -718,21 +981,21 @@ __global__ void head_stencil_kernel(const float* __restrict__ P, const float* __
   const int d = (int)((i / ((long long)W * H)) % D);
   const int co = (int)((i / ((long long)W * H * D)) % cout);
   const long long n = i / ((long long)W * H * D * cout);
-  const long long base = ((n * D + d) * H + h) * W + w;
+  const long long base = (n * D + d) * slice_stride + (long long)h * W + w;
   float acc = bias[co];
 #pragma unroll
-  for (int t = 0; t < 27; ++t) {
-    const int dd = t / 9 - 1, dh = (t / 3) % 3 - 1, dw = t % 3 - 1;
-    if ((unsigned)(d + dd) < (unsigned)D && (unsigned)(h + dh) < (unsigned)H && (unsigned)(w + dw) < (unsigned)W)
-      acc += P[(size_t)(t * cout + co) * row_stride + base + ((long long)dd * H + dh) * W + dw];
+  for (int t = 0; t < 9; ++t) {
+    const int dh = t / 3 - 1, dw = t % 3 - 1;
+    if ((unsigned)(h + dh) < (unsigned)H && (unsigned)(w + dw) < (unsigned)W)
+      acc += P[(size_t)(t * cout + co) * row_stride + base + (long long)dh * W + dw];
   }
   out[i] = act ? tanhf(acc) : acc;
 }
 void launch_head_stencil(const float* P, const float* bias, float* out, int N, int cout, int D, int H, int W,
-                         long long row_stride, int act, cudaStream_t st) {
+                         long long row_stride, long long slice_stride, int act, cudaStream_t st) {
   const long long total = (long long)N * cout * D * H * W;
-  launch_k(head_stencil_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, P, bias, out, cout, D, H, W, row_stride, act,
-           total);
+  launch_k(head_stencil_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, P, bias, out, cout, D, H, W, row_stride,
+           slice_stride, act, total);
 }
 
 // ------------------------------------------------------------------------------------------------

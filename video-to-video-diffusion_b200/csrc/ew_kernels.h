@@ -13,6 +13,16 @@ void launch_splitk_finalize(float* ws, const float* bias, __half* out, float* st
 void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st);
 void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
                       int T, int P, int C, int G, float eps, cudaStream_t st);
+// fused attention-followed ResBlock tail + TemporalAttention (see ew_kernels.cu)
+bool attn_fused_supported(int C);
+int attn_setup_kernels();  // opt-in to >48 KB dynamic shared memory; call once per device
+int attn_tsum_splits(int B, int T, int P, int C);
+void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, const float* gamma, const float* beta,
+                        int B, int T, int P, int C, int G, float eps, float* stats_out, int G_out, float* tsum, int TS,
+                        cudaStream_t st);
+void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* stats, const float* gamma,
+                          const float* beta, const __half* Wt, const float* bias, int B, int T, int P, int C, int G,
+                          float eps, cudaStream_t st);
 void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, cudaStream_t st);
 void launch_temb(const long long* t_ptr, const long long* t_table, const int* step_ptr, const float* freqs,
                  const float* W1, const float* b1, const float* W2, const float* b2, float* silu_temb,
@@ -36,7 +46,7 @@ void launch_pack_vae_enc_in(const float* v, __half* out, int B, int Cin, int Cpa
                             cudaStream_t st);
 void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dout, long long HW, cudaStream_t st);
 void launch_head_stencil(const float* P, const float* bias, float* out, int N, int cout, int D, int H, int W,
-                         long long row_stride, int act, cudaStream_t st);
+                         long long row_stride, long long slice_stride, int act, cudaStream_t st);
 void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const float* gd, const float* gh,
                               const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
                               int w0, cudaStream_t st);

@@ -3,6 +3,7 @@
 #include "unet.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b2v {
 
@@ -60,6 +61,13 @@ static int load_attn(AttnW& a, const WeightMap& wm, const std::string& pre, int 
   }
   std::string err;
   if (conv_layer_init(a.pv, CONV_K1, Wpv.data(), nullptr, C, 0, C, err)) return fail(pre + ": " + err);
+  // transposed fp16 copy for the fused attn_proj_add kernel: Wt[c][co] = Wpv[co][c]
+  std::vector<__half> wt((size_t)C * C);
+  for (int o = 0; o < C; ++o)
+    for (int i = 0; i < C; ++i) wt[(size_t)i * C + o] = conv_operand(Wpv[(size_t)o * C + i]);
+  a.Wt = (__half*)ds.alloc(wt.size() * sizeof(__half));
+  if (!a.Wt || cudaMemcpy(a.Wt, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(pre + ": device alloc failed for the folded attention weights");
   return 0;
 }
 
@@ -171,6 +179,11 @@ UNet::~UNet() {
 }
 
 // ------------------------------------------------------------------ program
+static bool attn_fused(int C) {
+  static const bool off = getenv("B2V_ATTN_UNFUSED") != nullptr;  // A/B switch: the four-launch form
+  return !off && attn_fused_supported(C);
+}
+
 struct UBuild {
   UNet& u;
   UProgram& up;
@@ -181,7 +194,9 @@ struct UBuild {
   }
 
   // ResBlock3D.forward (models/unet3d.py:116-133)
-  Act res(const std::string& name, const ResW& r, const Act& x, const Act* skip, float** out_stats, int G_out) {
+  // tsum_out != nullptr: the block feeds a TemporalAttention -- its tail also emits the depth sums (fused path)
+  Act res(const std::string& name, const ResW& r, const Act& x, const Act* skip, float** out_stats, int G_out,
+          float** tsum_out = nullptr, int* ts_out = nullptr) {
     float* s1 = b.new_stats(r.n1.G);
     Act y1 = b.conv(name + ".conv1", r.conv1, x, skip, s1, r.n1.G);
     Act rr;
@@ -192,14 +207,64 @@ struct UBuild {
     b.free(y1);
     float* so = out_stats ? b.new_stats(G_out) : nullptr;
     if (out_stats) *out_stats = so;
-    b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, -1, r.has_res ? &rr : &x, 1, so, G_out);
+    if (tsum_out && so && b.ok) {
+      const int B = up.B, T = y2.D, P = y2.H * y2.W, C = y2.C, G = r.n2.G;
+      const int TS = attn_tsum_splits(B, T, P, C);
+      float* tsum = (float*)b.pool.get((size_t)B * TS * P * C * sizeof(float));
+      if (!tsum) {
+        b.ok = false;
+        return y2;
+      }
+      *tsum_out = tsum;
+      *ts_out = TS;
+      __half* yp = y2.p;
+      const __half* rp = r.has_res ? rr.p : x.p;
+      const float *ga = r.n2.gamma, *be = r.n2.beta;
+      Op op;
+      op.name = name + ".gn2_res_silu_tsum";
+      op.bytes = (double)B * T * P * C * 2.0 * 3.0;
+      op.out = yp;
+      op.out_bytes = (size_t)B * T * P * C * 2;
+      op.run = [=](cudaStream_t st) {
+        launch_gn_res_tsum(yp, rp, s2, ga, be, B, T, P, C, G, 1e-5f, so, G_out, tsum, TS, st);
+      };
+      b.ops.push_back(std::move(op));
+    } else {
+      b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, -1, r.has_res ? &rr : &x, 1, so, G_out);
+    }
     if (r.has_res) b.free(rr);
     return y2;
   }
 
   // TemporalAttention.forward (models/unet3d.py:163-194), folded: x += Wpv * sum_t GN(x) + (T*u + bp)
-  void attn(const std::string& name, const AttnW& a, Act& x, const float* stats_x) {
+  void attn(const std::string& name, const AttnW& a, Act& x, const float* stats_x, float* tsum = nullptr, int TS = 0) {
     const int B = up.B, T = x.D, P = x.H * x.W, C = x.C;
+    if (tsum) {
+      std::vector<float> bias(C, 0.f);
+      for (int i = 0; i < C; ++i) bias[i] = (float)T * a.u[i] + a.bp[i];
+      const float* bias_d = up.ds.upload(bias);
+      if (!bias_d) {
+        b.ok = false;
+        return;
+      }
+      __half* xp = x.p;
+      const __half* wt = a.Wt;
+      const float *ga = a.norm.gamma, *be = a.norm.beta;
+      const int G = a.norm.G;
+      Op op;
+      op.name = name + ".proj_add";
+      op.bytes = (double)B * T * P * C * 2.0 * 2.0;
+      // algorithmic FLOPs of the reference block: qkv (C->3C) and proj (C->C) 1x1 convs over all T positions
+      op.flops = 2.0 * B * T * P * (double)C * (4.0 * C);
+      op.out = xp;
+      op.out_bytes = (size_t)B * T * P * C * 2;
+      op.run = [=](cudaStream_t st) {
+        launch_attn_proj_add(xp, tsum, TS, stats_x, ga, be, wt, bias_d, B, T, P, C, G, 1e-5f, st);
+      };
+      b.ops.push_back(std::move(op));
+      b.pool.put(tsum);
+      return;
+    }
     Act s = b.alloc(C, 1, x.H, x.W);
     if (!b.ok) return;
     {
@@ -304,10 +369,14 @@ static int build_unet_program(UNet& u, UProgram& up) {
     for (size_t i = 0; i < lv.res.size() && b.ok; ++i) {
       const std::string nm = "down" + std::to_string(l) + "." + std::to_string(i);
       const bool at = !lv.attn.empty();
-      Act nxt = ub.res(nm, lv.res[i], cur, nullptr, at ? &cur_stats : nullptr, at ? lv.attn[i].norm.G : 0);
+      float* tsum = nullptr;
+      int TS = 0;
+      const bool fz = at && attn_fused(lv.attn[i].C);
+      Act nxt = ub.res(nm, lv.res[i], cur, nullptr, at ? &cur_stats : nullptr, at ? lv.attn[i].norm.G : 0,
+                       fz ? &tsum : nullptr, &TS);
       b.free(cur);
       cur = nxt;
-      if (at) ub.attn(nm + ".attn", lv.attn[i], cur, cur_stats);
+      if (at) ub.attn(nm + ".attn", lv.attn[i], cur, cur_stats, tsum, TS);
     }
     skips.push_back(cur);
     cur_is_skip = true;
@@ -318,10 +387,13 @@ static int build_unet_program(UNet& u, UProgram& up) {
   }
   if (!b.ok) return -1;
   {
-    Act nxt = ub.res("mid1", u.mid1, cur, nullptr, &cur_stats, u.mid_attn.norm.G);
+    float* tsum = nullptr;
+    int TS = 0;
+    Act nxt = ub.res("mid1", u.mid1, cur, nullptr, &cur_stats, u.mid_attn.norm.G,
+                     attn_fused(u.mid_attn.C) ? &tsum : nullptr, &TS);
     if (!cur_is_skip) b.free(cur);
     cur = nxt;
-    ub.attn("mid.attn", u.mid_attn, cur, cur_stats);
+    ub.attn("mid.attn", u.mid_attn, cur, cur_stats, tsum, TS);
     nxt = ub.res("mid2", u.mid2, cur, nullptr, nullptr, 0);
     b.free(cur);
     cur = nxt;
@@ -335,18 +407,21 @@ static int build_unet_program(UNet& u, UProgram& up) {
       float** so = (at || last) ? &cur_stats : nullptr;
       const int Go = at ? lv.attn[i].norm.G : (last ? u.out_norm.G : 0);
       Act nxt;
+      float* tsum = nullptr;
+      int TS = 0;
+      float** tso = (at && attn_fused(lv.attn[i].C)) ? &tsum : nullptr;
       if (i == 0) {
         Act skip = skips.back();
         skips.pop_back();
-        nxt = ub.res(nm, lv.res[i], cur, &skip, so, Go);
+        nxt = ub.res(nm, lv.res[i], cur, &skip, so, Go, tso, &TS);
         b.free(skip);
       } else {
-        nxt = ub.res(nm, lv.res[i], cur, nullptr, so, Go);
+        nxt = ub.res(nm, lv.res[i], cur, nullptr, so, Go, tso, &TS);
       }
       b.free(cur);
       cur = nxt;
       if (at) {
-        ub.attn(nm + ".attn", lv.attn[i], cur, cur_stats);
+        ub.attn(nm + ".attn", lv.attn[i], cur, cur_stats, tsum, TS);
         if (last) {  // conv_out's GroupNorm needs statistics of the post-attention tensor
           cur_stats = b.new_stats(u.out_norm.G);
           const __half* xp = cur.p;

@@ -15,6 +15,7 @@ struct ResW {  // ResBlock3D (models/unet3d.py:77-133)
 struct AttnW {  // TemporalAttention (models/unet3d.py:136-194), folded
   GNW norm;
   ConvLayer pv;
+  __half* Wt = nullptr;  // [c][co] fp16 transpose of the folded Wp*Wv (fused attn_proj_add path; owned by UNet::ds)
   std::vector<float> u, bp;
   int C = 0;
 };

@@ -76,6 +76,21 @@ def gn_apply(y, stats, gamma, beta, groups, temb=None, res=None, mode=0, groups_
     return out, so
 
 
+def res_attn_tail(y, res, stats_in, gamma2, beta2, groups2, gamma_a, beta_a, groups_a, wpv, bias):
+    """Fused ResBlock tail + TemporalAttention: returns silu(GN(y)+res) + Wpv.sum_t GN_a(.) + bias (cl16, new tensor).
+    wpv: fp32 (C, C) folded projection [co][c]; bias: fp32 (C,)."""
+    B, D, H, W, C = y.shape
+    out = y.clone()
+    wt = wpv.t().contiguous().to(torch.float16)
+    sm = torch.zeros((B, groups_a, 2), dtype=torch.float32, device=y.device)
+    ws = torch.empty(B * 8 * H * W * C, dtype=torch.float32, device=y.device)
+    _lib.check(_lib.lib().b2v_res_attn_tail(
+        _lib.dptr(out, torch.float16), _lib.dptr(res, torch.float16), _lib.dptr(stats_in), _lib.dptr(gamma2),
+        _lib.dptr(beta2), groups2, _lib.dptr(gamma_a), _lib.dptr(beta_a), groups_a, _lib.dptr(wt, torch.float16),
+        _lib.dptr(bias), _lib.dptr(sm), _lib.dptr(ws), ws.numel(), B, D, H * W, C, _lib.stream()), "res_attn_tail")
+    return out
+
+
 def gn_stats(x, groups):
     B, D, H, W, C = x.shape
     st = torch.zeros((B, groups, 2), dtype=torch.float32, device=x.device)
