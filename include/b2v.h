@@ -151,7 +151,7 @@ int b2v_gn_stats(const void* x, int B, long long S, int C, int G, float* stats, 
  *   y <- silu(GN_G2(y) + res);  y <- y + Wpv * sum_t GN_Ga(y) + bias   (in place, cl16 [B][T][P][C])
  * wt: device fp16 [C][C], wt[c][co] = (Wproj*Wv)[co][c];  bias: device fp32 [C] = T*Wproj*bv + bproj
  * stats_mid: zeroed fp32 [B][Ga][2] (receives the statistics of the ResBlock output)
- * tsum_ws: fp32 workspace of tsum_cap >= B*8*P*C elements                                                      */
+ * tsum_ws: fp32 workspace of tsum_cap >= B*5*P*C elements                                                      */
 int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const float* gamma2, const float* beta2, int G2,
                       const float* gamma_a, const float* beta_a, int Ga, const void* wt, const float* bias,
                       float* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream);

@@ -277,16 +277,15 @@ int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const flo
                       const float* gamma_a, const float* beta_a, int Ga, const void* wt, const float* bias,
                       float* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream) {
   if (!attn_fused_supported(C)) return fail("res_attn_tail: unsupported channel count for the fused attention path");
-  static const int setup = attn_setup_kernels();
-  if (setup) return fail("res_attn_tail: cudaFuncSetAttribute failed");
   const int TS = attn_tsum_splits(B, T, P, C);
-  if ((long long)B * TS * P * C > tsum_cap) return fail("res_attn_tail: depth-sum workspace too small");
+  if ((long long)B * (TS + 1) * P * C > tsum_cap) return fail("res_attn_tail: depth-sum workspace too small");
+  __half* g_ws = (__half*)(tsum_ws + (size_t)B * TS * P * C);  // fp16 [B][P][C] behind the depth sums
   cudaStream_t st = (cudaStream_t)stream;
   launch_gn_res_tsum((__half*)y, (const __half*)res, stats_in, gamma2, beta2, B, T, P, C, G2, 1e-5f, stats_mid, Ga,
                      tsum_ws, TS, st);
-  launch_attn_proj_add((__half*)y, tsum_ws, TS, stats_mid, gamma_a, beta_a, (const __half*)wt, bias, B, T, P, C, Ga,
-                       1e-5f, st);
-  g_launches += 2;
+  launch_attn_proj_add((__half*)y, tsum_ws, TS, stats_mid, gamma_a, beta_a, (const __half*)wt, bias, g_ws, B, T, P, C,
+                       Ga, 1e-5f, st);
+  g_launches += 3;
   B2V_CUDA(cudaGetLastError());
   return 0;
 }

@@ -103,10 +103,6 @@ int conv_setup_kernels(std::string& err) {
     err = std::string("cudaFuncSetAttribute(conv_igemm): ") + cudaGetErrorString(e);
     return -1;
   }
-  if (attn_setup_kernels()) {
-    err = "cudaFuncSetAttribute(attn_proj_add) failed";
-    return -1;
-  }
   return 0;
 }
 
@@ -305,15 +301,20 @@ int conv_splitk_factor(const ConvLayer& L, int N, int D, int H, int W) {
   int gD, gH, gW, bw, bh, bd;
   out_grid(L, D, H, W, gD, gH, gW);
   choose_box(gW, gH, gD, bw, bh, bd);
-  const long long tiles = (long long)((gW + bw - 1) / bw) * ((gH + bh - 1) / bh) * ((gD + bd - 1) / bd) * N *
-                          (L.cout_pad / L.bn);
+  const long long m_tiles = (long long)((gW + bw - 1) / bw) * ((gH + bh - 1) / bh) * ((gD + bd - 1) / bd) * N;
+  const long long tiles = m_tiles * (L.cout_pad / L.bn);
   const int ksteps = L.ntaps * (L.cin0_pad + L.cin1_pad) / 64;
   const int sms = device_sm_count();
-  if (tiles * 2 > sms || ksteps < 32) return 1;
-  int S = (int)(sms / tiles);
-  if (S > ksteps / 16) S = ksteps / 16;
-  if (S > 8) S = 8;
-  return S < 2 ? 1 : S;
+  if (ksteps < 32) return 1;
+  if (tiles * 2 <= sms) {
+    int S = (int)(sms / tiles);
+    if (S > ksteps / 16) S = ksteps / 16;
+    if (S > 8) S = 8;
+    return S < 2 ? 1 : S;
+  }
+  // a partially filled single wave is NOT split (tried: the 6x6 level at batch 4, 56 CTA-pair units on 74 clusters cut
+  // into 5 k-slices -- the atomics and the finalize pass cost more than the idle SMs: 947 vs 932 ms per batch)
+  return 1;
 }
 size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
   if (conv_splitk_factor(L, N, D, H, W) < 2) return 0;
@@ -513,10 +514,10 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
   }
   // CTA pairs (cta_group::2) for the wide layers: a work unit is two consecutive m-tiles of one (class, n-tile)
   static const bool no_pair = getenv("B2V_NO_PAIR") != nullptr;
-  P.pair = !no_pair && !P.swapped && P.splitk == 1 && L.bn == 256 && sms >= 2;
+  P.pair = !no_pair && !P.swapped && L.bn == 256 && sms >= 2;
   if (P.pair) {
     const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N;
-    total = ((m_tiles + 1) / 2) * p.nclass * p.n_tiles;
+    total = ((m_tiles + 1) / 2) * p.nclass * p.n_tiles * P.splitk;
     const long long clusters = total < sms / 2 ? total : sms / 2;
     P.grid = (int)(2 * clusters);
   } else {
@@ -541,7 +542,8 @@ void conv_launch(const ConvPlan& P, cudaStream_t st) {
     return;
   }
   if (P.splitk > 1) {
-    switch (P.bn) {
+    if (P.pair) launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(192), ConvCfg<256, true>::SMEM, st, P.p);
+    else switch (P.bn) {
       case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(192), ConvCfg<64>::SMEM, st, P.p); break;
       case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
       default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;

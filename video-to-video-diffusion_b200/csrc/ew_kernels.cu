@@ -408,16 +408,14 @@ void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused form of the attention-followed ResBlock tail + TemporalAttention (two launches instead of four, and the
-// block output is read once less):
+// Fused form of the attention-followed ResBlock tail + TemporalAttention (the block output is read once less):
 //   gn_res_tsum   : y = silu(GN(y) + res) in place (ResBlock3D tail, mode 1 of gn_apply), statistics of the result for
 //                   the attention's GroupNorm, and the raw depth sums  tsum[b][ts][p][c] = sum_{t in split ts} y[b,t,p,c]
 //                   -- a thread owns one (position, 8-channel vector) and walks the depth axis, so the depth sum is a
 //                   register accumulation and doubles as the thread's contribution to the group sums
-//   attn_proj_add : s = gamma*rstd*(sum_ts tsum - T*mean) + T*beta ;  g = Wpv*s + (T*u + bp) ;  x[b,t,p,:] += g[p,:]
-//                   one CTA per PB positions: s and g live in shared memory, the C x C product runs on the CUDA cores
-//                   (2*C*C FLOP per position: 0.3 GFLOP per block at level 1 -- launch latency of a tensor-core GEMM
-//                   kernel was 3x its math time), the broadcast add streams the T slices.
+//   attn_gemm     : s = gamma*rstd*(sum_ts tsum - T*mean) + T*beta ;  g = Wpv*s + (T*u + bp)   on the CUDA cores
+//                   (2*C*C FLOP per position, 0.3 GFLOP per block at level 1: the fixed latency of the persistent
+//                   tensor-core kernel was 3x its math time); then add_bcast_t: x[b,t,p,:] += g[p,:]
 // ------------------------------------------------------------------------------------------------
 template <int U>
 __global__ void __launch_bounds__(256) gn_res_tsum_kernel(__half* y_, const __half* res_,
@@ -518,7 +516,7 @@ int attn_tsum_splits(int B, int T, int P, int C) {
   const int PB = 256 / C8 > 0 ? 256 / C8 : 1;
   const long long blocks = (long long)B * ((P + PB - 1) / PB);
   int TS = 1;
-  while (blocks * TS < 256 && TS * 2 <= T / 4) TS *= 2;
+  while (blocks * TS < 256 && TS * 2 <= T / 4 && TS < 4) TS *= 2;
   return TS;
 }
 
@@ -532,140 +530,131 @@ void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, con
            C, G, eps, stats_out, G_out, tsum);
 }
 
-template <int PB>
-__global__ void __launch_bounds__(512) attn_proj_add_kernel(__half* x_, const float* __restrict__ tsum, int TS,
-                                                            const float* __restrict__ stats,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta,
-                                                            const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
-                                                            const float* __restrict__ bias, int T, int P, int C, int G,
-                                                            float eps) {
+// g[b][p][co] = bias[co] + sum_c Wpv[co][c] * s[b][p][c],  s = gamma*rstd*(sum_ts tsum - T*mean) + T*beta  (fp16 out).
+// Tiled CUDA-core GEMM, weight-stationary per CTA: tile = 32 positions x 64 output channels, K chunks of 64 staged in
+// shared memory (the s operand is normalised on its way in), next chunk prefetched into registers while the current
+// one is multiplied.  Every weight is read ceil(P/32)*B times in total (a per-position-block C x C product re-read the
+// whole matrix in every CTA: 74 MB of same-address L2 traffic per launch, ~40 us).
+constexpr int AG_P = 32, AG_N = 64, AG_K = 64;
+template <int TS>
+__global__ void __launch_bounds__(256, 2) attn_gemm_kernel(const float* __restrict__ tsum, const float* __restrict__ stats,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
+                                                        const float* __restrict__ bias, __half* g_, int T, int P, int C,
+                                                        int G, float eps) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];  // s[PB][C], g[PB][C], part[NCG][PB][C]
-  const int C8 = C >> 3;
-  const int NCG = blockDim.x / C8;  // k-splits of the C x C product
-  const int CK = C / NCG;
-  const int b = blockIdx.y, p0 = blockIdx.x * PB;
-  float* s = sm;
-  float* gs = sm + PB * C;
-  float* part = sm + 2 * PB * C;
-  const int cpg = C / G;
-  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
-  for (int i = threadIdx.x; i < PB * C; i += blockDim.x) {
-    const int pl = i / C, c = i % C, p = p0 + pl;
-    float v = 0.f;
-    if (p < P)
-      for (int ts = 0; ts < TS; ++ts) v += tsum[(((size_t)b * TS + ts) * P + p) * C + c];
-    const int g = c / cpg;
-    const float su = stats[((size_t)b * G + g) * 2], ss = stats[((size_t)b * G + g) * 2 + 1];
-    const float mean = su * inv_n;
-    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
-    s[i] = gamma[c] * rstd * (v - (float)T * mean) + (float)T * beta[c];
-  }
-  __syncthreads();
-  {
-    // thread = (8 output channels, k-split): CK independent 16-byte weight loads (a warp reads whole 512-byte runs
-    // of one weight row), fp32 FMAs against the shared-memory s; partial sums meet in shared memory in a fixed order
-    const int cov = threadIdx.x % C8, cg = threadIdx.x / C8;
-    float acc[PB][8];
+  extern __shared__ float sdyn[];  // per-channel scale / shift of the normalisation: [2][C]
+  __shared__ float sS[AG_K][AG_P + 1];
+  __shared__ float sW[AG_K][AG_N];
+  float* s_scl = sdyn;
+  float* s_shf = sdyn + C;
+  const int b = blockIdx.z, p0 = blockIdx.x * AG_P, n0 = blockIdx.y * AG_N;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 4 output channels x 2 positions per thread
+  // loader roles: s -> (channel sc, positions spg + 4*i: 64 threads read one 256-byte run), w -> (k row wk + 32*i,
+  // 8 output channels).  fetch() only ISSUES loads (no arithmetic on the results), so the next chunk's global-memory
+  // latency overlaps the multiply of the current one; the normalisation happens when the registers are stashed.
+  const int sc = tid & 63, spg = tid >> 6;
+  const int wk = tid >> 3, wc = (tid & 7) * 8;
+  float rs[TS][8];
+  uint4 rw[2];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int k = 0; k < PB; ++k)
+    for (int ts = 0; ts < TS; ++ts)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-    const uint4* w8 = reinterpret_cast<const uint4*>(Wt) + (size_t)cg * CK * C8 + cov;
-    const float* sp = s + cg * CK;
-#pragma unroll 8
-    for (int c = 0; c < CK; ++c) {
+      for (int i = 0; i < 8; ++i) {
+        const int p = min(p0 + spg + 4 * i, P - 1);  // clamped: rows beyond P are never stored
+        rs[ts][i] = tsum[(((size_t)b * TS + ts) * P + p) * C + k0 + sc];
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      rw[i] = *reinterpret_cast<const uint4*>(Wt + (size_t)(k0 + wk + 32 * i) * C + n0 + wc);
+  };
+  auto stash = [&](int k0) {
+    const float scl = s_scl[k0 + sc], shf = s_shf[k0 + sc];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = rs[0][i];
+#pragma unroll
+      for (int ts = 1; ts < TS; ++ts) v += rs[ts][i];
+      sS[sc][spg + 4 * i] = fmaf(scl, v, shf);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
       float w[8];
-      h8_to_f(w8[(size_t)c * C8], w);
-#pragma unroll
-      for (int k = 0; k < PB; ++k) {
-        const float sv = sp[k * C + c];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(w[j], sv, acc[k][j]);
-      }
+      h8_to_f(rw[i], w);
+      float4* d = reinterpret_cast<float4*>(&sW[wk + 32 * i][wc]);
+      d[0] = make_float4(w[0], w[1], w[2], w[3]);
+      d[1] = make_float4(w[4], w[5], w[6], w[7]);
     }
-#pragma unroll
-    for (int k = 0; k < PB; ++k) {
-      float4* o = reinterpret_cast<float4*>(part + ((size_t)cg * PB + k) * C + cov * 8);
-      o[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-      o[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+  };
+  fetch(0);
+  {
+    const int cpg = C / G;
+    const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
+    for (int c = tid; c < C; c += 256) {
+      const int gi = c / cpg;
+      const float su = stats[((size_t)b * G + gi) * 2], ss = stats[((size_t)b * G + gi) * 2 + 1];
+      const float mean = su * inv_n;
+      const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+      const float scl = gamma[c] * rstd;
+      s_scl[c] = scl;
+      s_shf[c] = (float)T * (beta[c] - mean * scl);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < PB * C; i += blockDim.x) {
-    float a = bias[i % C];
-    for (int cg = 0; cg < NCG; ++cg) a += part[(size_t)cg * PB * C + i];
-    gs[i] = a;
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < C; k0 += AG_K) {
+    __syncthreads();  // previous chunk fully consumed (and, first time, the scale / shift table written)
+    stash(k0);
+    __syncthreads();
+    if (k0 + AG_K < C) fetch(k0 + AG_K);
+#pragma unroll 8
+    for (int k = 0; k < AG_K; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+      const float s0 = sS[k][ty * 2], s1 = sS[k][ty * 2 + 1];
+      acc[0][0] = fmaf(w.x, s0, acc[0][0]);
+      acc[0][1] = fmaf(w.y, s0, acc[0][1]);
+      acc[0][2] = fmaf(w.z, s0, acc[0][2]);
+      acc[0][3] = fmaf(w.w, s0, acc[0][3]);
+      acc[1][0] = fmaf(w.x, s1, acc[1][0]);
+      acc[1][1] = fmaf(w.y, s1, acc[1][1]);
+      acc[1][2] = fmaf(w.z, s1, acc[1][2]);
+      acc[1][3] = fmaf(w.w, s1, acc[1][3]);
+    }
   }
-  __syncthreads();
-  // x[b, t, p0 + pl, :] += g[pl, :]: rows (t, pl); for a fixed t the PB positions are one contiguous run
-  const int pbv = min(PB, P - p0);
-  const int cv = threadIdx.x % C8, r0 = threadIdx.x / C8, RPI = blockDim.x / C8;
-  const int rows = T * pbv;
-  uint4* x = reinterpret_cast<uint4*>(x_) + ((size_t)b * T * P + p0) * C8 + cv;
-  constexpr int U = 4;
-  for (int r = r0; r < rows; r += U * RPI) {
-    uint4 xv[U];
-    size_t off[U];
-    int pl[U];
+  const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      const int rr = r + k * RPI;
-      if (rr < rows) {
-        const int t = rr / pbv;
-        pl[k] = rr - t * pbv;
-        off[k] = ((size_t)t * P + pl[k]) * C8;
-        xv[k] = x[off[k]];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < U; ++k) {
-      if (r + k * RPI >= rows) break;
-      float f[8];
-      h8_to_f(xv[k], f);
-      const float4 g0 = *reinterpret_cast<const float4*>(gs + pl[k] * C + cv * 8);
-      const float4 g1 = *reinterpret_cast<const float4*>(gs + pl[k] * C + cv * 8 + 4);
-      f[0] += g0.x; f[1] += g0.y; f[2] += g0.z; f[3] += g0.w;
-      f[4] += g1.x; f[5] += g1.y; f[6] += g1.z; f[7] += g1.w;
-      x[off[k]] = f_to_h8(f);
-    }
+  for (int i = 0; i < 2; ++i) {
+    const int p = p0 + ty * 2 + i;
+    if (p >= P) continue;
+    const __half2 h0 = __floats2half2_rn(operand_round(acc[i][0] + bv.x), operand_round(acc[i][1] + bv.y));
+    const __half2 h1 = __floats2half2_rn(operand_round(acc[i][2] + bv.z), operand_round(acc[i][3] + bv.w));
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0);
+    u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(g_ + ((size_t)b * P + p) * C + n0 + tx * 4) = u;
   }
 }
 
-// 512 threads = C/8 channel vectors x 512/(C/8) k-splits, so C must be a multiple of 64 (and C/8 <= 256)
-bool attn_fused_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 2048 && 256 % (C / 8) == 0; }
+bool attn_fused_supported(int C) { return C % 64 == 0 && C >= 64 && C / 8 <= 256; }
 
-static size_t attn_proj_add_smem(int PB, int C) {
-  return (size_t)(2 * PB * C + (512 / (C / 8)) * PB * C) * sizeof(float);
-}
-
-int attn_setup_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(attn_proj_add_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attn_proj_add_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attn_proj_add_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  return e == cudaSuccess ? 0 : -1;
-}
-
+// the attention itself: g = Wpv * GN(sum_t x) + bias (attn_gemm), then x[b,t,p,:] += g[b,p,:] (add_bcast_t)
 void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* stats, const float* gamma,
-                          const float* beta, const __half* Wt, const float* bias, int B, int T, int P, int C, int G,
-                          float eps, cudaStream_t st) {
-  // positions per CTA: the most (<= 4, fewer re-reads of the C x C weights) that still gives about one CTA per SM
-  int pb = 1;
-  for (int c = 2; c <= 4; c *= 2)
-    if ((long long)B * ((P + c - 1) / c) >= 140) pb = c;
-  const dim3 grid((P + pb - 1) / pb, B);
-  const size_t smem = attn_proj_add_smem(pb, C);
-#define APA(PP)                                                                                                       \
-  launch_k(attn_proj_add_kernel<PP>, grid, dim3(512), smem, st, x, tsum, TS, stats, gamma, beta, Wt, bias, T, P, C, G, \
-           eps)
-  if (pb == 4) APA(4);
-  else if (pb == 2) APA(2);
-  else APA(1);
-#undef APA
+                          const float* beta, const __half* Wt, const float* bias, __half* g_ws, int B, int T, int P,
+                          int C, int G, float eps, cudaStream_t st) {
+  const dim3 grid((P + AG_P - 1) / AG_P, C / AG_N, B);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+#define AG(TT) launch_k(attn_gemm_kernel<TT>, grid, dim3(256), smem, st, tsum, stats, gamma, beta, Wt, bias, g_ws, T, P, C, G, eps)
+  if (TS == 1) AG(1);
+  else if (TS == 2) AG(2);
+  else AG(4);  // attn_tsum_splits returns 1, 2 or 4
+#undef AG
+  launch_add_bcast_t(x, g_ws, B, T, P, C, st);
 }
 
 // ------------------------------------------------------------------------------------------------

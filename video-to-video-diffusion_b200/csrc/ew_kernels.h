@@ -15,14 +15,13 @@ void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, c
                       int T, int P, int C, int G, float eps, cudaStream_t st);
 // fused attention-followed ResBlock tail + TemporalAttention (see ew_kernels.cu)
 bool attn_fused_supported(int C);
-int attn_setup_kernels();  // opt-in to >48 KB dynamic shared memory; call once per device
 int attn_tsum_splits(int B, int T, int P, int C);
 void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, const float* gamma, const float* beta,
                         int B, int T, int P, int C, int G, float eps, float* stats_out, int G_out, float* tsum, int TS,
                         cudaStream_t st);
 void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* stats, const float* gamma,
-                          const float* beta, const __half* Wt, const float* bias, int B, int T, int P, int C, int G,
-                          float eps, cudaStream_t st);
+                          const float* beta, const __half* Wt, const float* bias, __half* g_ws, int B, int T, int P,
+                          int C, int G, float eps, cudaStream_t st);
 void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, cudaStream_t st);
 void launch_temb(const long long* t_ptr, const long long* t_table, const int* step_ptr, const float* freqs,
                  const float* W1, const float* b1, const float* W2, const float* b2, float* silu_temb,

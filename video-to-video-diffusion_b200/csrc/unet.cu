@@ -210,7 +210,8 @@ struct UBuild {
     if (tsum_out && so && b.ok) {
       const int B = up.B, T = y2.D, P = y2.H * y2.W, C = y2.C, G = r.n2.G;
       const int TS = attn_tsum_splits(B, T, P, C);
-      float* tsum = (float*)b.pool.get((size_t)B * TS * P * C * sizeof(float));
+      // depth sums [B][TS][P][C] fp32, followed by the attention GEMM's fp16 output [B][P][C]
+      float* tsum = (float*)b.pool.get((size_t)B * (TS + 1) * P * C * sizeof(float));
       if (!tsum) {
         b.ok = false;
         return y2;
@@ -258,8 +259,10 @@ struct UBuild {
       op.flops = 2.0 * B * T * P * (double)C * (4.0 * C);
       op.out = xp;
       op.out_bytes = (size_t)B * T * P * C * 2;
+      op.launches = 2;
+      __half* g_ws = (__half*)(tsum + (size_t)B * TS * P * C);
       op.run = [=](cudaStream_t st) {
-        launch_attn_proj_add(xp, tsum, TS, stats_x, ga, be, wt, bias_d, B, T, P, C, G, 1e-5f, st);
+        launch_attn_proj_add(xp, tsum, TS, stats_x, ga, be, wt, bias_d, g_ws, B, T, P, C, G, 1e-5f, st);
       };
       b.ops.push_back(std::move(op));
       b.pool.put(tsum);

@@ -83,7 +83,7 @@ def res_attn_tail(y, res, stats_in, gamma2, beta2, groups2, gamma_a, beta_a, gro
     out = y.clone()
     wt = wpv.t().contiguous().to(torch.float16)
     sm = torch.zeros((B, groups_a, 2), dtype=torch.float32, device=y.device)
-    ws = torch.empty(B * 8 * H * W * C, dtype=torch.float32, device=y.device)
+    ws = torch.empty(B * 5 * H * W * C, dtype=torch.float32, device=y.device)
     _lib.check(_lib.lib().b2v_res_attn_tail(
         _lib.dptr(out, torch.float16), _lib.dptr(res, torch.float16), _lib.dptr(stats_in), _lib.dptr(gamma2),
         _lib.dptr(beta2), groups2, _lib.dptr(gamma_a), _lib.dptr(beta_a), groups_a, _lib.dptr(wt, torch.float16),
