@@ -381,18 +381,18 @@ void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, c
            T, P, C, G, eps);
 }
 
-__global__ void add_bcast_t_kernel(__half* x_, const __half* __restrict__ y_, int T, long long PC8, long long total) {
+__global__ void add_bcast_t_kernel(__half* x_, const __half* __restrict__ y_, int T, int PC8) {
   pdl_trigger();
   pdl_wait();
-  uint4* x = reinterpret_cast<uint4*>(x_);
-  const uint4* y = reinterpret_cast<const uint4*>(y_);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / (T * PC8);
-    const long long r = i % PC8;
+  // grid.y = sample; 32-bit index math (a 64-bit divide per element made the kernel issue-bound)
+  const int b = blockIdx.y;
+  uint4* x = reinterpret_cast<uint4*>(x_) + (size_t)b * T * PC8;
+  const uint4* y = reinterpret_cast<const uint4*>(y_) + (size_t)b * PC8;
+  const int total = T * PC8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     float a[8], c[8];
     h8_to_f(x[i], a);
-    h8_to_f(y[b * PC8 + r], c);
+    h8_to_f(y[i % PC8], c);
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] += c[j];
     x[i] = f_to_h8(a);
@@ -400,11 +400,12 @@ __global__ void add_bcast_t_kernel(__half* x_, const __half* __restrict__ y_, in
 }
 
 void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, cudaStream_t st) {
-  const long long PC8 = (long long)P * (C / 8);
-  const long long total = (long long)B * T * PC8;
+  const int PC8 = P * (C / 8);
+  const long long total = (long long)T * PC8;
   int blocks = cdiv(total, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  launch_k(add_bcast_t_kernel, dim3(blocks), dim3(256), 0, st, x, y, T, PC8, total);
+  const int cap = (148 * 16 + B - 1) / B;
+  if (blocks > cap) blocks = cap;
+  launch_k(add_bcast_t_kernel, dim3(blocks, B), dim3(256), 0, st, x, y, T, PC8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,56 +536,56 @@ void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, con
 // shared memory (the s operand is normalised on its way in), next chunk prefetched into registers while the current
 // one is multiplied.  Every weight is read ceil(P/32)*B times in total (a per-position-block C x C product re-read the
 // whole matrix in every CTA: 74 MB of same-address L2 traffic per launch, ~40 us).
-constexpr int AG_P = 32, AG_N = 64, AG_K = 64;
+constexpr int AG_P = 32, AG_N = 64, AG_K = 64, AG_T = 128;
 template <int TS>
-__global__ void __launch_bounds__(256, 2) attn_gemm_kernel(const float* __restrict__ tsum, const float* __restrict__ stats,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
-                                                        const float* __restrict__ bias, __half* g_, int T, int P, int C,
-                                                        int G, float eps) {
+__global__ void __launch_bounds__(AG_T) attn_gemm_kernel(const float* __restrict__ tsum, const float* __restrict__ stats,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
+                                                         const float* __restrict__ bias, __half* g_, int T, int P, int C,
+                                                         int G, float eps) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sdyn[];  // per-channel scale / shift of the normalisation: [2][C]
-  __shared__ float sS[AG_K][AG_P + 1];
-  __shared__ float sW[AG_K][AG_N];
+  __shared__ __align__(16) float sS[AG_P][AG_K + 4];  // [position][k]
+  __shared__ __align__(16) float sW[AG_K][AG_N];      // [k][output channel]
   float* s_scl = sdyn;
   float* s_shf = sdyn + C;
   const int b = blockIdx.z, p0 = blockIdx.x * AG_P, n0 = blockIdx.y * AG_N;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // 4 output channels x 2 positions per thread
-  // loader roles: s -> (channel sc, positions spg + 4*i: 64 threads read one 256-byte run), w -> (k row wk + 32*i,
+  const int tx = tid & 15, ty = tid >> 4;  // register tile: 4 output channels x 4 positions per thread
+  // loader roles: s -> (channel sc, positions spg + 2*i: 64 threads read one 256-byte run), w -> (k row wk + 16*i,
   // 8 output channels).  fetch() only ISSUES loads (no arithmetic on the results), so the next chunk's global-memory
   // latency overlaps the multiply of the current one; the normalisation happens when the registers are stashed.
   const int sc = tid & 63, spg = tid >> 6;
   const int wk = tid >> 3, wc = (tid & 7) * 8;
-  float rs[TS][8];
-  uint4 rw[2];
+  float rs[TS][16];
+  uint4 rw[4];
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int ts = 0; ts < TS; ++ts)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int p = min(p0 + spg + 4 * i, P - 1);  // clamped: rows beyond P are never stored
+      for (int i = 0; i < 16; ++i) {
+        const int p = min(p0 + spg + 2 * i, P - 1);  // clamped: rows beyond P are never stored
         rs[ts][i] = tsum[(((size_t)b * TS + ts) * P + p) * C + k0 + sc];
       }
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-      rw[i] = *reinterpret_cast<const uint4*>(Wt + (size_t)(k0 + wk + 32 * i) * C + n0 + wc);
+    for (int i = 0; i < 4; ++i)
+      rw[i] = *reinterpret_cast<const uint4*>(Wt + (size_t)(k0 + wk + 16 * i) * C + n0 + wc);
   };
   auto stash = [&](int k0) {
     const float scl = s_scl[k0 + sc], shf = s_shf[k0 + sc];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
       float v = rs[0][i];
 #pragma unroll
       for (int ts = 1; ts < TS; ++ts) v += rs[ts][i];
-      sS[sc][spg + 4 * i] = fmaf(scl, v, shf);
+      sS[spg + 2 * i][sc] = fmaf(scl, v, shf);
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       float w[8];
       h8_to_f(rw[i], w);
-      float4* d = reinterpret_cast<float4*>(&sW[wk + 32 * i][wc]);
+      float4* d = reinterpret_cast<float4*>(&sW[wk + 16 * i][wc]);
       d[0] = make_float4(w[0], w[1], w[2], w[3]);
       d[1] = make_float4(w[4], w[5], w[6], w[7]);
     }
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(256, 2) attn_gemm_kernel(const float* __restri
   {
     const int cpg = C / G;
     const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
-    for (int c = tid; c < C; c += 256) {
+    for (int c = tid; c < C; c += AG_T) {
       const int gi = c / cpg;
       const float su = stats[((size_t)b * G + gi) * 2], ss = stats[((size_t)b * G + gi) * 2 + 1];
       const float mean = su * inv_n;
@@ -603,9 +604,9 @@ __global__ void __launch_bounds__(256, 2) attn_gemm_kernel(const float* __restri
       s_shf[c] = (float)T * (beta[c] - mean * scl);
     }
   }
-  float acc[2][4];
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < C; k0 += AG_K) {
@@ -613,27 +614,32 @@ __global__ void __launch_bounds__(256, 2) attn_gemm_kernel(const float* __restri
     stash(k0);
     __syncthreads();
     if (k0 + AG_K < C) fetch(k0 + AG_K);
-#pragma unroll 8
-    for (int k = 0; k < AG_K; ++k) {
-      const float4 w = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
-      const float s0 = sS[k][ty * 2], s1 = sS[k][ty * 2 + 1];
-      acc[0][0] = fmaf(w.x, s0, acc[0][0]);
-      acc[0][1] = fmaf(w.y, s0, acc[0][1]);
-      acc[0][2] = fmaf(w.z, s0, acc[0][2]);
-      acc[0][3] = fmaf(w.w, s0, acc[0][3]);
-      acc[1][0] = fmaf(w.x, s1, acc[1][0]);
-      acc[1][1] = fmaf(w.y, s1, acc[1][1]);
-      acc[1][2] = fmaf(w.z, s1, acc[1][2]);
-      acc[1][3] = fmaf(w.w, s1, acc[1][3]);
+#pragma unroll 4
+    for (int k4 = 0; k4 < AG_K; k4 += 4) {
+      float4 sv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sv[j] = *reinterpret_cast<const float4*>(&sS[ty * 4 + j][k4]);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 w = *reinterpret_cast<const float4*>(&sW[k4 + kk][tx * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float sj = kk == 0 ? sv[j].x : kk == 1 ? sv[j].y : kk == 2 ? sv[j].z : sv[j].w;
+          acc[j][0] = fmaf(w.x, sj, acc[j][0]);
+          acc[j][1] = fmaf(w.y, sj, acc[j][1]);
+          acc[j][2] = fmaf(w.z, sj, acc[j][2]);
+          acc[j][3] = fmaf(w.w, sj, acc[j][3]);
+        }
+      }
     }
   }
   const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int p = p0 + ty * 2 + i;
+  for (int j = 0; j < 4; ++j) {
+    const int p = p0 + ty * 4 + j;
     if (p >= P) continue;
-    const __half2 h0 = __floats2half2_rn(operand_round(acc[i][0] + bv.x), operand_round(acc[i][1] + bv.y));
-    const __half2 h1 = __floats2half2_rn(operand_round(acc[i][2] + bv.z), operand_round(acc[i][3] + bv.w));
+    const __half2 h0 = __floats2half2_rn(operand_round(acc[j][0] + bv.x), operand_round(acc[j][1] + bv.y));
+    const __half2 h1 = __floats2half2_rn(operand_round(acc[j][2] + bv.z), operand_round(acc[j][3] + bv.w));
     uint2 u;
     u.x = *reinterpret_cast<const uint32_t*>(&h0);
     u.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -649,7 +655,7 @@ void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* sta
                           int C, int G, float eps, cudaStream_t st) {
   const dim3 grid((P + AG_P - 1) / AG_P, C / AG_N, B);
   const size_t smem = 2 * (size_t)C * sizeof(float);
-#define AG(TT) launch_k(attn_gemm_kernel<TT>, grid, dim3(256), smem, st, tsum, stats, gamma, beta, Wt, bias, g_ws, T, P, C, G, eps)
+#define AG(TT) launch_k(attn_gemm_kernel<TT>, grid, dim3(AG_T), smem, st, tsum, stats, gamma, beta, Wt, bias, g_ws, T, P, C, G, eps)
   if (TS == 1) AG(1);
   else if (TS == 2) AG(2);
   else AG(4);  // attn_tsum_splits returns 1, 2 or 4
@@ -960,31 +966,34 @@ void launch_upsample_depth(const float* in, float* out, int BC, int Din, int Dou
 // ------------------------------------------------------------------------------------------------
 __global__ void head_stencil_kernel(const float* __restrict__ P, const float* __restrict__ bias, float* out,
                                     int cout, int D, int H, int W, long long row_stride, long long slice_stride,
-                                    int act, long long total) {
+                                    int act, int planes) {
   pdl_trigger();
   pdl_wait();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (n, co, d, h, w)
-  if (i >= total) return;
-  const int w = (int)(i % W);
-  const int h = (int)((i / W) % H);
-  const int d = (int)((i / ((long long)W * H)) % D);
-  const int co = (int)((i / ((long long)W * H * D)) % cout);
-  const long long n = i / ((long long)W * H * D * cout);
-  const long long base = (n * D + d) * slice_stride + (long long)h * W + w;
-  float acc = bias[co];
+  // grid.y walks the (n, co, d) planes, grid.x * block = position in the plane: only 32-bit index math per thread
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= H * W) return;
+  const int h = hw / W, w = hw - h * W;
+  const long long tap_stride = (long long)cout * row_stride;
+  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {  // plane = (n * cout + co) * D + d
+    const int d = plane % D;
+    const int co = (plane / D) % cout;
+    const int n = plane / (D * cout);
+    const float* base = P + (long long)co * row_stride + ((long long)n * D + d) * slice_stride + hw;
+    float acc = bias[co];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int dh = t / 3 - 1, dw = t % 3 - 1;
-    if ((unsigned)(h + dh) < (unsigned)H && (unsigned)(w + dw) < (unsigned)W)
-      acc += P[(size_t)(t * cout + co) * row_stride + base + (long long)dh * W + dw];
+    for (int t = 0; t < 9; ++t) {
+      const int dh = t / 3 - 1, dw = t % 3 - 1;
+      if ((unsigned)(h + dh) < (unsigned)H && (unsigned)(w + dw) < (unsigned)W)
+        acc += base[t * tap_stride + (long long)(dh * W + dw)];
+    }
+    out[(size_t)plane * H * W + hw] = act ? tanhf(acc) : acc;
   }
-  out[i] = act ? tanhf(acc) : acc;
 }
 void launch_head_stencil(const float* P, const float* bias, float* out, int N, int cout, int D, int H, int W,
                          long long row_stride, long long slice_stride, int act, cudaStream_t st) {
-  const long long total = (long long)N * cout * D * H * W;
-  launch_k(head_stencil_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, P, bias, out, cout, D, H, W, row_stride,
-           slice_stride, act, total);
+  const int planes = N * cout * D;
+  launch_k(head_stencil_kernel, dim3(cdiv((long long)H * W, 256), planes < 65535 ? planes : 65535), dim3(256), 0, st, P,
+           bias, out, cout, D, H, W, row_stride, slice_stride, act, planes);
 }
 
 // ------------------------------------------------------------------------------------------------
