@@ -130,6 +130,56 @@ def cpu_baseline(threads=None):
             "seconds_per_volume": t_vol}
 
 
+def gpu_eager_baseline(dev, batch=BATCH):
+    """the reference's own software path on the SAME GPU -- the oracle port composes exactly the
+    ATen/cuDNN ops the reference's eager PyTorch modules launch (NCDHW, one kernel per op) -- in true fp32 and with
+    PyTorch's default TF32 convolutions.  Bounded sample: 3 U-Net evaluations + 1 VAE encode + 1 VAE decode at the
+    bench batch; patch-volume time = (51 * t_unet + t_enc + t_dec) / batch.  Opt-in (--gpu-eager-baseline)."""
+    from oracle import ref_port as R
+    from v2v_b200.models import VideoToVideoDiffusion
+    cfg = load_cfg()
+    torch.manual_seed(0)
+    sd = {k: w.to(dev) for k, w in VideoToVideoDiffusion(cfg).eval().state_dict().items()}
+    vae_cfg, unet_cfg, _ = R.resolve_config(cfg)
+    usd = {k[5:]: w for k, w in sd.items() if k.startswith("unet.")}
+    vsd = {k[4:]: w for k, w in sd.items() if k.startswith("vae.")}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn((batch, 8, T_OUT, HW // 4, HW // 4), generator=g).to(dev)
+    c = torch.randn((batch, 8, T_OUT, HW // 4, HW // 4), generator=g).to(dev)
+    v = (torch.rand((batch, 1, T_IN, HW, HW), generator=g) * 2 - 1).to(dev)
+    t = torch.full((batch,), 500, device=dev)
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / n
+
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                t_unet = timed(lambda: R.unet_forward(usd, unet_cfg, x, t, c), 3)
+                t_enc = timed(lambda: R.vae_encode(vsd, v, vae_cfg["scaling_factor"]), 1)
+                t_dec = timed(lambda: R.vae_decode(vsd, x, vae_cfg["scaling_factor"]), 1)
+                t_batch = (DDIM_STEPS + 1) * t_unet + t_enc + t_dec
+                out[name] = {"value": round(batch / t_batch, 4), "unit": UNIT, "unet_step_ms": round(1e3 * t_unet, 2),
+                             "vae_encode_ms": round(1e3 * t_enc, 1), "vae_decode_ms": round(1e3 * t_dec, 1)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["sample"] = (f"eager PyTorch (oracle port = the reference's ATen op sequence) on the same GPU, batch {batch}: "
+                     "3 U-Net evals + 1 encode + 1 decode, volume time = (51*unet + enc + dec) / batch (extrapolated)")
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -289,6 +339,10 @@ def run_gpu(args, rank, world, local_rank):
         "whole_job_tflops": round(value * TF_PER_VOLUME, 1),
         "whole_job_frac_of_peak": round(value * TF_PER_VOLUME / world / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4),
     }
+    if world == 1 and args.gpu_eager_baseline:
+        del model
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline()
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -302,6 +356,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the reference's eager PyTorch op sequence on the same GPU (fp32 and TF32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
