@@ -390,7 +390,7 @@ static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int 
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
               void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws,
               float* splitk_ws) {
-  memset(&P, 0, sizeof(P));
+  P = ConvPlan();
   ConvParams& p = P.p;
   P.bn = L.bn;
   P.splitk = 1;

@@ -180,11 +180,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       if constexpr (MODE == 1) {
-        // raw rows: TMEM lane = (tap, cout) row, columns = positions.  A 32x32 fp32 block is transposed through
+        // raw rows: TMEM lane = (kh, kw, cout) row, columns = positions.  A 32x32 fp32 block is transposed through
         // shared memory (row pitch 33: conflict-free both ways) so that every store instruction writes one full
-        // 128-byte line of ONE row (16-byte pieces scattered over 27+ rows made DRAM writes crawl once P outgrew L2)
+        // 128-byte line of ONE row (16-byte pieces scattered over many rows made DRAM writes crawl once P outgrew L2)
         // logical row r of a 128-row tile sits in TMEM lane (r % 4) * 32 + r / 4 (weights are packed that way), so
-        // the valid rows of a narrow head (27 for Cout = 1) are spread over all four epilogue warps
+        // the valid rows of a narrow head (9 for Cout = 1) are spread over all four epilogue warps
         const int tbase = (tile / pairs) * 128;
         const int rows_in_tile = min(128, p.cout_valid - tbase);
         float* xf = reinterpret_cast<float*>(xpose) + (warp - 2) * (32 * 33);
@@ -203,11 +203,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
             pbase[(size_t)(tbase + rr * 4 + q) * (size_t)p.sC + pos0] = xf[rr * 33 + lane];
           __syncwarp();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-        continue;
-      }
+      } else {
 #pragma unroll 1
       for (int ci = 0; ci < 8; ++ci) {
         // this lane's "own" position of the chunk: row r of box (ci >> 2)
@@ -262,6 +258,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         }
         __syncwarp();
       }
+      }  // MODE
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
