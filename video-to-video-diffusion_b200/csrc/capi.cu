@@ -276,6 +276,8 @@ int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* g
 int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const float* gamma2, const float* beta2, int G2,
                       const float* gamma_a, const float* beta_a, int Ga, const void* wt, const float* bias,
                       float* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream) {
+  if (B < 0 || T < 0 || P < 0) return fail("res_attn_tail: negative extent");
+  if (B == 0 || T == 0 || P == 0) return 0;  // empty batch / volume: nothing to do
   if (!attn_fused_supported(C)) return fail("res_attn_tail: unsupported channel count for the fused attention path");
   const int TS = attn_tsum_splits(B, T, P, C);
   if ((long long)B * (TS + 1) * P * C > tsum_cap) return fail("res_attn_tail: depth-sum workspace too small");
