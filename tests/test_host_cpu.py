@@ -23,7 +23,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert not missing, missing
     assert set(_lib.SIGNATURES) == declared  # the ctypes binding covers the whole header, and nothing else
     L = _lib.lib()
-    assert L.b2v_abi_version() == 1 and L.b2v_launch_count() == 0
+    assert L.b2v_abi_version() == 2 and L.b2v_launch_count() == 0
 
 
 def test_c_abi_has_no_torch_or_cpu_fallback_dependency():

@@ -94,8 +94,11 @@ def test_conv_vs_torch(cuda_dev, case, groups):
     # epilogue statistics = (sum, sumsq) per (sample, group) of the fp32 result
     rg = ref.reshape(N, groups, -1)
     ref_stats = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1)
-    ok, msg = _report(name + ".stats", stats, ref_stats, 2e-3)
+    ok, msg = _report(name + ".stats", ops.stats_to_float(stats).float(), ref_stats, 2e-3)
     assert ok, msg
+    # integer (fixed-point) accumulation across CTAs: a second run gives bit-identical output and statistics
+    out2, stats2 = conv(x0, x1, groups=groups)
+    assert torch.equal(out2, out) and torch.equal(stats2, stats), name
 
 
 @pytest.mark.parametrize("cout,tanh", [(8, False), (1, True), (4, False)])
@@ -139,8 +142,12 @@ def test_gn_apply_vs_torch(cuda_dev, C, G, mode):
     assert ok, msg
     rg = got.reshape(B, Gout, -1)
     ref_so = torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1)
-    ok, msg = _report("gn.stats_out", so, ref_so, 1e-3)
+    ok, msg = _report("gn.stats_out", ops.stats_to_float(so).float(), ref_so, 1e-3)
     assert ok, msg
+    again = ops.gn_apply(y16, stats, gamma, beta, G, temb=temb if mode == 0 else None,
+                         res=ops.to_cl16(res) if mode == 1 else None, mode=mode, groups_out=Gout)
+    assert torch.equal(again[0], out) and torch.equal(again[1], so)
+    assert torch.equal(ops.gn_stats(y16, G), stats)
 
 
 @pytest.mark.parametrize("C,T,H,W,B", [(256, 12, 6, 6, 2), (512, 8, 3, 3, 1), (128, 5, 5, 7, 2), (64, 48, 4, 4, 1)])

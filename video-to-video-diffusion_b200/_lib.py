@@ -5,7 +5,7 @@ missing or no sm_100 device is present every call raises.  torch is used for dev
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint64, c_void_p
 
 import torch
 
@@ -31,6 +31,13 @@ class VAEDesc(ctypes.Structure):
     _fields_ = [("in_channels", c_int), ("latent_dim", c_int), ("base_channels", c_int), ("scaling_factor", c_float)]
 
 
+class SamplerCfg(ctypes.Structure):
+    """b2v_sampler_cfg: the schedule tables b2v_generate runs its sampler with (host pointers; noise is a device pointer)"""
+    _fields_ = [("sampler", c_int), ("n", c_int), ("timesteps", POINTER(c_int64)), ("alphas_cumprod", POINTER(c_float)),
+                ("n_train", c_int), ("eta", c_float), ("ddpm_coef", POINTER(c_float)), ("noise", c_void_p),
+                ("seed", c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/b2v.h one to one
 _P = c_void_p
 SIGNATURES = {
@@ -47,6 +54,14 @@ SIGNATURES = {
     "b2v_sampler_begin": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "b2v_ddpm_step": (c_int, [_P, c_int64, POINTER(c_float), _P, _P]),
     "b2v_sampler_end": (c_int, [_P, _P, _P]),
+    "b2v_ddpm_sample": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, POINTER(c_float), c_int, _P, c_uint64, _P]),
+    "b2v_ddpm_run": (c_int, [_P, POINTER(c_float), c_int, c_int, c_int, _P, c_uint64, _P]),
+    "b2v_ddim_timesteps": (c_int, [c_int, c_int, POINTER(c_int64), c_int]),
+    "b2v_philox_normal": (c_int, [_P, c_uint64, c_int, c_longlong, _P]),
+    "b2v_generate": (c_int, [_P, _P, POINTER(SamplerCfg), _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "b2v_q_sample": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_longlong, _P]),
+    "b2v_eps_mse_ws_bytes": (c_size_t, [c_int]),
+    "b2v_eps_mse": (c_int, [_P, _P, _P, _P, _P, c_size_t, c_int, c_longlong, c_longlong, _P]),
     "b2v_vae_create": (c_int, [POINTER(_P), POINTER(VAEDesc)]),
     "b2v_vae_destroy": (None, [_P]),
     "b2v_vae_load_weight": (c_int, [_P, c_char_p, _P, POINTER(c_int64), c_int]),
@@ -90,7 +105,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.b2v_abi_version() != 1:
+        if handle.b2v_abi_version() != 2:
             raise RuntimeError("libb2v.so ABI version mismatch; rebuild it")
         _lib = handle
     return _lib

@@ -8,6 +8,11 @@ using namespace b2v;
 
 struct b2v_unet {
   UNet u;
+  float* gen_ws = nullptr;  // scratch of b2v_generate (input copy, latents), grown on demand
+  size_t gen_cap = 0;
+  ~b2v_unet() {
+    if (gen_ws) cudaFree(gen_ws);
+  }
 };
 struct b2v_vae {
   VAE v;
@@ -89,6 +94,112 @@ int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise,
   return u->u.ddpm_step((long long)t, coef, noise, (cudaStream_t)stream);
 }
 int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) { return u->u.sampler_end(z_out, (cudaStream_t)stream); }
+int b2v_ddpm_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
+                    const float* coef, int n, const float* noise, uint64_t seed, void* stream) {
+  return u->u.ddpm_sample(z_init, cond, z_out, B, T, h, w, coef, n, noise, (unsigned long long)seed,
+                          (cudaStream_t)stream);
+}
+int b2v_ddpm_run(b2v_unet* u, const float* coef, int n, int first, int count, const float* noise, uint64_t seed,
+                 void* stream) {
+  return u->u.ddpm_run(coef, n, first, count, noise, (unsigned long long)seed, (cudaStream_t)stream);
+}
+int b2v_ddim_timesteps(int n_train, int steps, int64_t* out, int cap) {
+  if (n_train < 1 || steps < 1 || steps > n_train || !out) return fail("ddim_timesteps: bad arguments");
+  const int stride = n_train / steps;  // np.arange(0, n_train, n_train // steps)
+  std::vector<int64_t> ts;
+  for (int t = 0; t < n_train; t += stride) ts.push_back(t);
+  if (ts.back() != n_train - 1) ts.push_back(n_train - 1);
+  if ((int)ts.size() > cap) return fail("ddim_timesteps: output buffer too small");
+  for (size_t i = 0; i < ts.size(); ++i) out[i] = ts[ts.size() - 1 - i];
+  return (int)ts.size();
+}
+int b2v_philox_normal(float* out, uint64_t seed, int step, long long n, void* stream) {
+  if (check_device()) return -1;
+  if (n <= 0) return 0;
+  launch_philox_fill(out, (unsigned long long)seed, step, n, (cudaStream_t)stream);
+  g_launches += 1;
+  return check_launches("philox_normal");
+}
+
+// ------------------------------------------------------------------ end to end (models/model.py:230-343)
+int b2v_generate(b2v_unet* u, b2v_vae* v, const b2v_sampler_cfg* cfg, const float* v_in, const float* z_init,
+                 float* v_out, int B, int T_in, int T_out, int H, int W, int* nan_flag, void* stream) {
+  if (!u || !v || !cfg || !v_in || !z_init || !v_out) return fail("generate: null argument");
+  if (B < 0 || T_in < 1 || T_out < 1 || H < 4 || W < 4 || H % 4 || W % 4) return fail("generate: bad shape");
+  if (B == 0) return 0;
+  if (u->u.desc.latent_dim != v->v.desc.latent_dim) return fail("generate: U-Net / VAE latent_dim mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = v->v.desc.latent_dim, Cin = v->v.desc.in_channels, h = H / 4, w = W / 4;
+  const size_t n_v = (size_t)B * Cin * T_in * H * W, n_zi = (size_t)B * L * T_in * h * w,
+               n_z = (size_t)B * L * T_out * h * w, n_out = (size_t)B * Cin * T_out * H * W;
+  const size_t need = (n_v + n_zi + 2 * n_z) * sizeof(float) + 256;
+  if (need > u->gen_cap) {
+    B2V_CUDA(cudaStreamSynchronize(st));
+    if (u->gen_ws) cudaFree(u->gen_ws);
+    u->gen_ws = nullptr;
+    u->gen_cap = 0;
+    B2V_CUDA(cudaMalloc(&u->gen_ws, need));
+    u->gen_cap = need;
+  }
+  float* vc = u->gen_ws;
+  float* z_in = vc + n_v;
+  float* cond = z_in + n_zi;
+  float* z0 = cond + n_z;
+  int* flag = reinterpret_cast<int*>(z0 + n_z);  // [0]: the generate() checkpoints, [1]: the sampler's own guards
+  B2V_CUDA(cudaMemsetAsync(flag, 0, 2 * sizeof(int), st));
+  B2V_CUDA(cudaMemcpyAsync(vc, v_in, n_v * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  launch_guard(vc, (long long)n_v, 0, flag, st);
+  if (v->v.encode(vc, z_in, B, T_in, H, W, st)) return -1;
+  launch_guard(z_in, (long long)n_zi, 1, flag, st);
+  const float* c = z_in;
+  if (T_out != T_in) {
+    launch_upsample_depth(z_in, cond, B * L, T_in, T_out, (long long)h * w, st);
+    launch_guard(cond, (long long)n_z, 1, flag, st);
+    g_launches += 2;
+    c = cond;
+  }
+  if (cfg->sampler == 0) {
+    if (u->u.ddim_sample(z_init, c, z0, B, T_out, h, w, (const long long*)cfg->timesteps, cfg->n, cfg->alphas_cumprod,
+                         cfg->n_train, cfg->eta, cfg->noise, flag + 1, st))
+      return -1;
+  } else if (cfg->sampler == 1) {
+    if (u->u.ddpm_sample(z_init, c, z0, B, T_out, h, w, cfg->ddpm_coef, cfg->n, cfg->noise,
+                         (unsigned long long)cfg->seed, st))
+      return -1;
+  } else {
+    return fail("generate: unknown sampler (0 = ddim, 1 = ddpm)");
+  }
+  launch_guard(z0, (long long)n_z, 1, flag, st);
+  if (v->v.decode(z0, v_out, B, T_out, h, w, st)) return -1;
+  launch_guard(v_out, (long long)n_out, 1, flag, st);
+  g_launches += 4;
+  if (nan_flag) {
+    launch_or_flag(flag, flag + 1, st);
+    g_launches += 1;
+    B2V_CUDA(cudaMemcpyAsync(nan_flag, flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  return check_launches("generate");
+}
+
+int b2v_q_sample(const float* z0, const float* noise, const int64_t* t, const float* sqrt_ac, const float* sqrt_1m_ac,
+                 float* zt, int B, long long per_sample, void* stream) {
+  if (check_device()) return -1;
+  if (B <= 0 || per_sample <= 0) return 0;
+  launch_q_sample(z0, noise, (const long long*)t, sqrt_ac, sqrt_1m_ac, zt, B, per_sample, (cudaStream_t)stream);
+  g_launches += 1;
+  return check_launches("q_sample");
+}
+size_t b2v_eps_mse_ws_bytes(int B) { return eps_mse_ws_bytes(B < 1 ? 1 : B); }
+int b2v_eps_mse(const float* eps_pred, const float* noise, const float* mask, float* out, void* ws, size_t ws_bytes,
+                int B, long long per_sample, long long HW, void* stream) {
+  if (check_device()) return -1;
+  if (B <= 0 || per_sample <= 0) return 0;
+  if (HW <= 0 || per_sample % HW) return fail("eps_mse: per_sample must be a multiple of HW");
+  if (!ws || ws_bytes < eps_mse_ws_bytes(B)) return fail("eps_mse: workspace too small (b2v_eps_mse_ws_bytes)");
+  launch_eps_mse(eps_pred, noise, mask, B, per_sample, HW, (double*)ws, out, (cudaStream_t)stream);
+  g_launches += 2;
+  return check_launches("eps_mse");
+}
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream) {
   if (!u->u.last) return fail("unet_profile: run a forward first");
   u->u.last->temb = TembSource{u->u.last->proj, u->u.last->desc_rows, nullptr, 0};
@@ -220,7 +331,7 @@ void b2v_conv_destroy(b2v_conv* c) {
   }
   delete c;
 }
-int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, float* stats, int groups,
+int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, int64_t* stats, int groups,
                      int act_tanh, int N, int D, int H, int W, void* stream) {
   ConvPlan P;
   std::string err;
@@ -243,7 +354,7 @@ int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, i
     B2V_CUDA(cudaMemset(c->sk, 0, need_sk));
     c->sk_bytes = need_sk;
   }
-  if (conv_plan(P, c->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, out_fp32 ? OUT_F32 : OUT_CL16, stats,
+  if (conv_plan(P, c->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, out_fp32 ? OUT_F32 : OUT_CL16, (long long*)stats,
                 groups, act_tanh ? ACT_TANH : ACT_NONE, err, need_ws ? c->ws : nullptr, need_sk ? c->sk : nullptr))
     return fail(err);
   conv_launch(P, (cudaStream_t)stream);
@@ -263,19 +374,19 @@ int b2v_cl16_to_nc32(const void* in, float* out, int B, int C, int Cpad, long lo
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
-int b2v_gn_apply(const void* y, void* out, const float* stats_in, const float* gamma, const float* beta,
-                 const float* temb, const void* res, int B, long long S, int C, int G, int mode, float* stats_out,
+int b2v_gn_apply(const void* y, void* out, const int64_t* stats_in, const float* gamma, const float* beta,
+                 const float* temb, const void* res, int B, long long S, int C, int G, int mode, int64_t* stats_out,
                  int G_out, void* stream) {
   if (C % 8 || C / 8 > 256) return fail("gn_apply: C must be a multiple of 8 and <= 2048");
-  launch_gn_apply((const __half*)y, (__half*)out, stats_in, gamma, beta, temb, C, (const __half*)res, B, S, C, G, 1e-5f,
-                  mode, stats_out, G_out, (cudaStream_t)stream, nullptr, 0);
+  launch_gn_apply((const __half*)y, (__half*)out, (const stat_t*)stats_in, gamma, beta, temb, C, (const __half*)res, B, S,
+                  C, G, 1e-5f, mode, (stat_t*)stats_out, G_out, (cudaStream_t)stream, nullptr, 0);
   g_launches += 1;
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
-int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const float* gamma2, const float* beta2, int G2,
+int b2v_res_attn_tail(void* y, const void* res, const int64_t* stats_in, const float* gamma2, const float* beta2, int G2,
                       const float* gamma_a, const float* beta_a, int Ga, const void* wt, const float* bias,
-                      float* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream) {
+                      int64_t* stats_mid, float* tsum_ws, long long tsum_cap, int B, int T, int P, int C, void* stream) {
   if (B < 0 || T < 0 || P < 0) return fail("res_attn_tail: negative extent");
   if (B == 0 || T == 0 || P == 0) return 0;  // empty batch / volume: nothing to do
   if (!attn_fused_supported(C)) return fail("res_attn_tail: unsupported channel count for the fused attention path");
@@ -283,16 +394,17 @@ int b2v_res_attn_tail(void* y, const void* res, const float* stats_in, const flo
   if ((long long)B * (TS + 1) * P * C > tsum_cap) return fail("res_attn_tail: depth-sum workspace too small");
   __half* g_ws = (__half*)(tsum_ws + (size_t)B * TS * P * C);  // fp16 [B][P][C] behind the depth sums
   cudaStream_t st = (cudaStream_t)stream;
-  launch_gn_res_tsum((__half*)y, (const __half*)res, stats_in, gamma2, beta2, B, T, P, C, G2, 1e-5f, stats_mid, Ga,
+  launch_gn_res_tsum((__half*)y, (const __half*)res, (const stat_t*)stats_in, gamma2, beta2, B, T, P, C, G2, 1e-5f,
+                     (stat_t*)stats_mid, Ga,
                      tsum_ws, TS, st);
-  launch_attn_proj_add((__half*)y, tsum_ws, TS, stats_mid, gamma_a, beta_a, (const __half*)wt, bias, g_ws, B, T, P, C,
+  launch_attn_proj_add((__half*)y, tsum_ws, TS, (const stat_t*)stats_mid, gamma_a, beta_a, (const __half*)wt, bias, g_ws, B, T, P, C,
                        Ga, 1e-5f, st);
   g_launches += 3;
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
-int b2v_gn_stats(const void* x, int B, long long S, int C, int G, float* stats, void* stream) {
-  launch_gn_stats((const __half*)x, B, S, C, G, stats, (cudaStream_t)stream);
+int b2v_gn_stats(const void* x, int B, long long S, int C, int G, int64_t* stats, void* stream) {
+  launch_gn_stats((const __half*)x, B, S, C, G, (stat_t*)stats, (cudaStream_t)stream);
   g_launches += 1;
   B2V_CUDA(cudaGetLastError());
   return 0;

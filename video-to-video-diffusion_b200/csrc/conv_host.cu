@@ -320,7 +320,7 @@ size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W) {
   if (conv_splitk_factor(L, N, D, H, W) < 2) return 0;
   int gD, gH, gW;
   out_grid(L, D, H, W, gD, gH, gW);
-  return (size_t)N * gD * gH * gW * L.cout * sizeof(float);
+  return (size_t)conv_splitk_factor(L, N, D, H, W) * N * gD * gH * gW * L.cout * sizeof(float);  // one slab per split
 }
 
 // tap-GEMM position tiles: 128 consecutive (h, w) positions of one depth slice; slices are padded to whole tiles
@@ -388,7 +388,7 @@ static int plan_tapgemm(ConvPlan& P, const ConvLayer& L, const __half* in0, int 
 }
 
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws,
+              void* out, int out_mode, long long* stats, int groups, int act, std::string& err, float* tap_ws,
               float* splitk_ws) {
   P = ConvPlan();
   ConvParams& p = P.p;
@@ -501,8 +501,10 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
     if (S > 1) {
       P.splitk = p.splitk = S;
       p.ws = splitk_ws;
+      p.ws_slab = (long long)N * gD * gH * gW * L.cout;
       total *= S;
       P.fin.ws = splitk_ws;
+      P.fin.slab = p.ws_slab;
       P.fin.bias = L.bias;
       P.fin.out = (__half*)out;
       P.fin.stats = stats;
@@ -548,7 +550,8 @@ void conv_launch(const ConvPlan& P, cudaStream_t st) {
       case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
       default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
     }
-    launch_splitk_finalize(P.fin.ws, P.fin.bias, P.fin.out, P.fin.stats, P.fin.B, P.fin.S, P.fin.C, P.fin.G, st);
+    launch_splitk_finalize(P.fin.ws, P.fin.slab, P.splitk, P.fin.bias, P.fin.out, P.fin.stats, P.fin.B, P.fin.S,
+                           P.fin.C, P.fin.G, st);
     return;
   }
   if (P.pair) {

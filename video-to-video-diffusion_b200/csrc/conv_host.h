@@ -50,13 +50,15 @@ struct ConvPlan {
     int N, cout, D, H, W, act;
     long long row_stride, slice_stride;
   } st;
-  // split-K (small-M layers): the conv kernel adds fp32 partial tiles into fin.ws, fin describes the finalize pass
+  // split-K (small-M layers): the conv kernel stores fp32 partial tiles into per-split slabs of fin.ws, fin describes the
+  // finalize pass that sums them
   int splitk = 1;
   struct {
     float* ws;
+    long long slab;
     const float* bias;
     __half* out;
-    float* stats;
+    long long* stats;
     long long S;
     int C, G, B;
   } fin;
@@ -71,7 +73,7 @@ void conv_layer_free(ConvLayer& L);
 // in0/in1: NDHWC fp16 [N][D][H][W][cin*_pad]; (D,H,W) are the INPUT dims.
 // out_mode OUT_CL16: out is NDHWC fp16 with cout channels; OUT_F32: out is NCDHW fp32 with cout channels.
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
-              void* out, int out_mode, float* stats, int groups, int act, std::string& err, float* tap_ws = nullptr,
+              void* out, int out_mode, long long* stats, int groups, int act, std::string& err, float* tap_ws = nullptr,
               float* splitk_ws = nullptr);
 // k-split factor the planner would use for this layer / input (1 = none) and the fp32 workspace it needs
 int conv_splitk_factor(const ConvLayer& L, int N, int D, int H, int W);

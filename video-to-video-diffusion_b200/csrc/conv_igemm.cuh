@@ -32,7 +32,7 @@ struct ConvCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*group stats*/;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*group stats, per warp*/;
 };
 
 // Sum N per-lane values across the 32 lanes of a warp with N-1 + log2(32/N) shuffles (instead of 5 per value):
@@ -58,8 +58,10 @@ __device__ __forceinline__ float multi_reduce(float (&v)[N], int lane) {
   return v[0];
 }
 
-// per-(sample, group) sum / sum-of-squares of one 32-column chunk, accumulated into the CTA's shared-memory
-// table (flushed to global memory with one atomic per group when the CTA moves to another sample / n-tile)
+// per-(sample, group) sum / sum-of-squares of one 32-column chunk, accumulated into THIS WARP's shared-memory
+// table (the four tables are folded in a fixed order and flushed to global memory with one fixed-point atomic per
+// group when the CTA moves to another sample / n-tile).  Every table entry is only ever updated by one lane of its
+// warp, in program order, so the accumulation order -- and with it the fp32 result -- is the same in every run.
 template <int SUB>  // columns per group inside the chunk: min(channels-per-group, 32)
 __device__ __forceinline__ void chunk_stats(const float* v, bool valid, float* sstat, int glocal, int lane) {
   constexpr int SEGS = 32 / SUB, N = 2 * SEGS, LOG = (N == 32) ? 5 : (N == 16) ? 4 : (N == 8) ? 3 : (N == 4) ? 2 : 1;
@@ -77,13 +79,13 @@ __device__ __forceinline__ void chunk_stats(const float* v, bool valid, float* s
     acc[2 * seg + 1] = ss;
   }
   const float tot = multi_reduce<N>(acc, lane);
-  if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(&sstat[glocal * 2 + (lane >> (5 - LOG))], tot);
+  if ((lane & ((32 >> LOG) - 1)) == 0) sstat[glocal * 2 + (lane >> (5 - LOG))] += tot;
 }
 
 // Split-K for small-M layers (few output tiles, e.g. the 6x6 level at batch 1: 28 tiles on 148 SMs): work unit =
-// (tile, k-split); every unit accumulates its slice of the (tap, chunk) loop and adds its fp32 partial tile into a
-// zero-initialised workspace with vector atomics; splitk_finalize_kernel then applies bias, statistics and the fp16
-// conversion (and re-zeroes the workspace).  splitk == 1 is the ordinary path.
+// (tile, k-split); every unit accumulates its slice of the (tap, chunk) loop and stores its fp32 partial tile into
+// ITS OWN slab of the workspace (plain vector stores); splitk_finalize_kernel sums the slabs in a fixed order and
+// applies bias, statistics and the fp16 conversion -- deterministic, unlike atomics.  splitk == 1 is the ordinary path.
 __device__ __forceinline__ int unit_k0(int unit, int ksteps, int S) { return (int)((long long)(unit % S) * ksteps / S); }
 __device__ __forceinline__ int unit_k1(int unit, int ksteps, int S) {
   return (int)((long long)(unit % S + 1) * ksteps / S);
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // [<=128 groups][2]
+  float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // [4 epilogue warps][<=128 groups][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, Cfg::TM_COLS);
     else tmem_alloc(tmem_slot, Cfg::TM_COLS);
   }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   else __syncthreads();
@@ -248,14 +250,15 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     const int et = threadIdx.x - 64;           // 0..127 within the epilogue warps
     const int ng = (BN + p.cpg - 1) / p.cpg;   // groups touched by one n-tile
     int cur_key = -1, cur_nb = 0, cur_g0 = 0;
-    // flush the CTA-local group statistics: one global atomic per (group, moment)
+    float* wstat = sstat + (warp - 2) * 256;  // this warp's table
+    // flush the CTA-local group statistics: one global fixed-point atomic per (group, moment)
     auto flush = [&]() {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et < 2 * ng) {
-        const float val = sstat[et];
-        sstat[et] = 0.f;
+        const float val = ((sstat[et] + sstat[256 + et]) + sstat[512 + et]) + sstat[768 + et];
+        sstat[et] = sstat[256 + et] = sstat[512 + et] = sstat[768 + et] = 0.f;
         const int g = cur_g0 + (et >> 1);
-        if (g < p.groups) atomicAdd(p.stats + ((size_t)cur_nb * p.groups + g) * 2 + (et & 1), val);
+        if (g < p.groups) stat_add(p.stats + ((size_t)cur_nb * p.groups + g) * 2 + (et & 1), val);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -307,11 +310,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         tmem_ld_wait();
         const int cg = n0 + c0;
         if (cg >= p.cout_valid) break;
-        if (p.splitk > 1) {  // partial tile: fp32 vector atomics into the workspace (same NDHWC indexing as the output)
+        if (p.splitk > 1) {  // partial tile -> this k-split's slab of the workspace (same NDHWC indexing as the output)
           if (valid) {
-            float4* wsp = reinterpret_cast<float4*>(p.ws + roff + cg);
+            float4* wsp = reinterpret_cast<float4*>(p.ws + (long long)(unit % p.splitk) * p.ws_slab + roff + cg);
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) atomicAdd(wsp + j / 4, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            for (int j = 0; j < CH; j += 4) wsp[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           continue;
         }
@@ -320,11 +323,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         if constexpr (CH == 32) {
           if (p.stats && p.splitk == 1) {
             const int gl = cg / p.cpg - cur_g0;
-            if (p.cpg >= 32) chunk_stats<32>(v, valid, sstat, gl, lane);
-            else if (p.cpg == 16) chunk_stats<16>(v, valid, sstat, gl, lane);
-            else if (p.cpg == 8) chunk_stats<8>(v, valid, sstat, gl, lane);
-            else if (p.cpg == 4) chunk_stats<4>(v, valid, sstat, gl, lane);
-            else chunk_stats<2>(v, valid, sstat, gl, lane);
+            if (p.cpg >= 32) chunk_stats<32>(v, valid, wstat, gl, lane);
+            else if (p.cpg == 16) chunk_stats<16>(v, valid, wstat, gl, lane);
+            else if (p.cpg == 8) chunk_stats<8>(v, valid, wstat, gl, lane);
+            else if (p.cpg == 4) chunk_stats<4>(v, valid, wstat, gl, lane);
+            else chunk_stats<2>(v, valid, wstat, gl, lane);
           }
         }
         if (p.act == ACT_TANH) {

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
       if (et < 2 * ng) {
         const float val = sstat[et];
         sstat[et] = 0.f;
-        atomicAdd(p.stats + ((size_t)cur_nb * p.groups + (et >> 1)) * 2 + (et & 1), val);
+        stat_add(p.stats + ((size_t)cur_nb * p.groups + (et >> 1)) * 2 + (et & 1), val);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
             s += __shfl_xor_sync(0xffffffffu, s, o);
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
           }
+          // a group is owned by ONE lane of ONE warp (cpg <= 32 adjacent channels): plain read-modify-write in
+          // program order, so the CTA's partial sums are built in the same order in every run
           if ((lane & (p.cpg - 1)) == 0) {
-            atomicAdd(&sstat[(ch / p.cpg) * 2], s);
-            atomicAdd(&sstat[(ch / p.cpg) * 2 + 1], ss);
+            sstat[(ch / p.cpg) * 2] += s;
+            sstat[(ch / p.cpg) * 2 + 1] += ss;
           }
         }
         // 32 channels x 32 positions -> [position][channel] through shared memory, then 16-byte row stores

@@ -17,7 +17,7 @@ struct ConvParams {
   long long sN, sD, sH, sW, sC;  // output strides (elements)
   void* out;
   const float* bias;      // [n_tiles*BN]
-  float* stats;           // [batch][groups][2] (sum, sumsq) or nullptr
+  long long* stats;       // [batch][groups][2] (sum, sumsq) as Q43.20 fixed point (stat_t, ptx.cuh) or nullptr
   int bw, bh, bd, rows_valid;
   int tiles_w, tiles_h, tiles_d, batch;
   int n_tiles, nclass, ntaps;
@@ -25,7 +25,8 @@ struct ConvParams {
   int W, H, D;            // logical grid of output positions per sample and class
   int groups, cpg, cout_valid, out_mode, act;
   int splitk;             // k-splits per output tile (1 = off)
-  float* ws;              // split-K fp32 workspace, NDHWC like the output
+  float* ws;              // split-K fp32 workspace: splitk slabs, each NDHWC like the output
+  long long ws_slab;      // elements per slab
 };
 
 }  // namespace b2v

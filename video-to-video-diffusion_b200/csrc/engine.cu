@@ -13,6 +13,23 @@ int fail(const std::string& msg) {
   return -1;
 }
 
+static thread_local cudaError_t g_launch_err = cudaSuccess;
+void note_launch_error(cudaError_t e) {
+  if (g_launch_err == cudaSuccess) g_launch_err = e;
+}
+cudaError_t take_launch_error() {
+  const cudaError_t e = g_launch_err;
+  g_launch_err = cudaSuccess;
+  return e;
+}
+// status of everything launched since the last check: a failed cudaLaunchKernelEx first, then the runtime's last error
+int check_launches(const char* what) {
+  cudaError_t e = take_launch_error();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
 const HostTensor* need(const WeightMap& wm, const std::string& key, long long numel) {
   auto it = wm.find(key);
   if (it == wm.end()) {
@@ -29,17 +46,35 @@ const HostTensor* need(const WeightMap& wm, const std::string& key, long long nu
 
 float* DeviceStore::upload(const float* h, size_t n) {
   float* d = nullptr;
-  if (cudaMalloc(&d, n * sizeof(float)) != cudaSuccess) return nullptr;
-  cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMalloc(&d, (n ? n : 1) * sizeof(float));
+  if (e == cudaSuccess && n) e = cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {  // a failed upload must not leave uninitialised weights behind a success code
+    if (d) cudaFree(d);
+    fail(std::string("device upload failed: ") + cudaGetErrorString(e));
+    return nullptr;
+  }
   ptrs.push_back(d);
   return d;
 }
 void* DeviceStore::alloc(size_t bytes) {
   void* d = nullptr;
-  if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
-  cudaMemset(d, 0, bytes);
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 1);
+  if (e == cudaSuccess && bytes) e = cudaMemset(d, 0, bytes);
+  if (e != cudaSuccess) {
+    if (d) cudaFree(d);
+    fail(std::string("device allocation failed: ") + cudaGetErrorString(e));
+    return nullptr;
+  }
   ptrs.push_back(d);
   return d;
+}
+void DeviceStore::release(void* p) {
+  for (size_t i = 0; i < ptrs.size(); ++i)
+    if (ptrs[i] == p) {
+      cudaFree(p);
+      ptrs.erase(ptrs.begin() + i);
+      return;
+    }
 }
 DeviceStore::~DeviceStore() {
   for (void* p : ptrs) cudaFree(p);
@@ -82,8 +117,7 @@ Program::~Program() {
 int Program::run_eager(cudaStream_t st) {
   for (auto& op : ops) op.run(st);
   g_launches += launches;
-  B2V_CUDA(cudaGetLastError());
-  return 0;
+  return check_launches("program launch");
 }
 
 int Program::run(cudaStream_t st) {
@@ -103,6 +137,8 @@ int Program::run(cudaStream_t st) {
     if (e == cudaSuccess) {
       for (auto& op : ops) op.run(cs);
       e = cudaStreamEndCapture(cs, &g);
+      const cudaError_t le = take_launch_error();
+      if (e == cudaSuccess) e = le;
     }
     if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, g, 0);
     if (g) cudaGraphDestroy(g);
@@ -135,7 +171,7 @@ int Program::profile(int iters, cudaStream_t st, std::string& json) const {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  B2V_CUDA(cudaGetLastError());
+  if (check_launches("profile")) return -1;
   json = "[";
   char buf[512];
   for (size_t i = 0; i < ops.size(); ++i) {
@@ -192,19 +228,19 @@ void Builder::free(Act& a) {
   if (a.p) pool.put(a.p);
   a.p = nullptr;
 }
-float* Builder::new_stats(int G) {
+stat_t* Builder::new_stats(int G) {
   const size_t n = (size_t)B * G * 2;
   if (stats_used + n > stats_cap) {
     fail("statistics arena exhausted");
     ok = false;
     return stats_base;
   }
-  float* s = stats_base + stats_used;
+  stat_t* s = stats_base + stats_used;
   stats_used += n;
   return s;
 }
 
-Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, float* stats,
+Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, stat_t* stats,
                   int groups, float* out_fp32, int act, const float* bias_override) {
   Act out;
   int oD = in0.D, oH = in0.H, oW = in0.W;
@@ -239,9 +275,14 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
     sk_ws = (float*)ds->alloc(sk_bytes);
     sk_cap = sk_ws ? sk_bytes : 0;
   }
+  // the conv epilogue folds statistics with power-of-two shuffles; other group widths (e.g. model_channels 192 ->
+  // 24 channels per group) take a separate statistics pass over the fp16 output
+  const int cpg = (stats && groups > 0) ? L.cout / groups : 0;
+  const bool epi_stats = stats && cpg >= 2 && !(cpg & (cpg - 1)) && (L.bn + cpg - 1) / cpg <= 64 && !out_fp32;
   const int rc = conv_plan(P, L, in0.p, in1 ? in1->p : nullptr, B, in0.D, in0.H, in0.W,
-                           out_fp32 ? (void*)out_fp32 : (void*)out.p, out_fp32 ? OUT_F32 : OUT_CL16, stats, groups, act,
-                           err, ws, (sk_bytes && sk_ws) ? sk_ws : nullptr);
+                           out_fp32 ? (void*)out_fp32 : (void*)out.p, out_fp32 ? OUT_F32 : OUT_CL16,
+                           epi_stats ? stats : nullptr, epi_stats ? groups : 0, act, err, ws,
+                           (sk_bytes && sk_ws) ? sk_ws : nullptr);
   if (ws) pool.put(ws);
   if (rc) {
     fail(name + ": " + err);
@@ -261,11 +302,21 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
   op.out_bytes = out_fp32 ? (size_t)B * L.cout * oD * oH * oW * 4 : (size_t)B * oD * oH * oW * L.cout * 2;
   op.run = [P](cudaStream_t st) { conv_launch(P, st); };
   ops.push_back(std::move(op));
+  if (stats && !epi_stats && !out_fp32) {
+    const __half* xp = out.p;
+    const long long S = out.S();
+    const int C = out.C, Bc = B;
+    Op so;
+    so.name = name + ".stats";
+    so.bytes = (double)B * S * C * 2.0;
+    so.run = [=](cudaStream_t st) { launch_gn_stats(xp, Bc, S, C, groups, stats, st); };
+    ops.push_back(std::move(so));
+  }
   return out;
 }
 
-void Builder::gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, int temb_off,
-                       const Act* res, int mode, float* stats_out, int G_out) {
+void Builder::gn_apply(const std::string& name, Act& y, const stat_t* stats_in, const GNW& g, int temb_off,
+                       const Act* res, int mode, stat_t* stats_out, int G_out) {
   const int Bc = B;
   const long long S = y.S();
   const int C = y.C;

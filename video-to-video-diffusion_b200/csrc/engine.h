@@ -16,6 +16,7 @@ namespace b2v {
 extern thread_local std::string g_err;
 extern std::atomic<long long> g_launches;
 int fail(const std::string& msg);  // sets g_err, returns -1
+int check_launches(const char* what);  // first failed launch since the last check / cudaGetLastError -> fail()
 #define B2V_CUDA(x)                                                                       \
   do {                                                                                    \
     cudaError_t e__ = (x);                                                                \
@@ -40,7 +41,8 @@ struct DeviceStore {
   std::vector<void*> ptrs;
   float* upload(const float* h, size_t n);
   float* upload(const std::vector<float>& h) { return upload(h.data(), h.size()); }
-  void* alloc(size_t bytes);
+  void* alloc(size_t bytes);   // zero-initialised; nullptr (and g_err) on failure
+  void release(void* p);       // free one array early (tables that are re-grown)
   ~DeviceStore();
 };
 
@@ -107,23 +109,23 @@ struct Builder {
   std::vector<Op>& ops;
   Pool& pool;
   int B;
-  float* stats_base;
+  stat_t* stats_base;  // Q43.20 fixed-point (sum, sumsq) pairs, see ptx.cuh
   size_t stats_cap, stats_used = 0;
   bool ok = true;
   const TembSource* temb_src = nullptr;  // U-Net programs only
   DeviceStore* ds = nullptr;             // owner of the zero-initialised split-K workspace
   float* sk_ws = nullptr;
   size_t sk_cap = 0;
-  Builder(std::vector<Op>& o, Pool& p, int b, float* sb, size_t sc) : ops(o), pool(p), B(b), stats_base(sb), stats_cap(sc) {}
+  Builder(std::vector<Op>& o, Pool& p, int b, stat_t* sb, size_t sc) : ops(o), pool(p), B(b), stats_base(sb), stats_cap(sc) {}
   Act alloc(int C, int D, int H, int W);
   void free(Act& a);
-  float* new_stats(int G);
+  stat_t* new_stats(int G);
   // out_fp32 != nullptr: NCDHW fp32 head; otherwise returns a fresh cl16 activation
-  Act conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, float* stats, int groups,
+  Act conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, stat_t* stats, int groups,
            float* out_fp32 = nullptr, int act = ACT_NONE, const float* bias_override = nullptr);
   // temb_off >= 0: add row offset temb_off of the time-embedding table (*temb_src) after the SiLU (mode 0)
-  void gn_apply(const std::string& name, Act& y, const float* stats_in, const GNW& g, int temb_off, const Act* res,
-                int mode, float* stats_out, int G_out);
+  void gn_apply(const std::string& name, Act& y, const stat_t* stats_in, const GNW& g, int temb_off, const Act* res,
+                int mode, stat_t* stats_out, int G_out);
 };
 
 }  // namespace b2v

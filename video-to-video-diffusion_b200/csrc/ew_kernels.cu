@@ -50,6 +50,55 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
   return u;
 }
 
+// Per-channel scale / shift of a GroupNorm for the 8 channels c0..c0+7 of sample b: y*sc + sh = gamma*(y-mean)*rstd + beta
+__device__ __forceinline__ void gn_scale_shift(const stat_t* __restrict__ stats, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int b, int G, int cpg, double inv_n,
+                                               float eps, int c0, float (&sc)[8], float (&sh)[8]) {
+  int gprev = -1;
+  float mean = 0.f, rstd = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    if (g != gprev) {
+      stat_mean_rstd(stats + ((size_t)b * G + g) * 2, inv_n, eps, mean, rstd);
+      gprev = g;
+    }
+    const float ga = gamma[c];
+    sc[j] = ga * rstd;
+    sh[j] = beta[c] - mean * ga * rstd;
+  }
+}
+
+// Deterministic block reduction of per-thread partial sums (thread (cv, rr) holds 8 channels of row-slice rr) into the
+// per-(sample, group) fixed-point statistics: row slices are folded in index order, then the channels of each group
+// in index order, so the CTA's contribution is the same fp32 number in every run; the cross-CTA sum is an integer
+// atomic (order-independent).  sm: [(R + 1)][2][C] floats.  All threads of the block must call it.
+__device__ __forceinline__ void block_stats_out(const float (&as)[8], const float (&ass)[8], float* sm, int C, int R,
+                                                int cv, int rr, int b, int G_out, stat_t* stats_out) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sm[(size_t)(rr * 2) * C + cv * 8 + j] = as[j];
+    sm[(size_t)(rr * 2 + 1) * C + cv * 8 + j] = ass[j];
+  }
+  __syncthreads();
+  float* tot = sm + (size_t)R * 2 * C;  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int m = i / C, c = i - m * C;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += sm[(size_t)(r * 2 + m) * C + c];
+    tot[i] = s;
+  }
+  __syncthreads();
+  const int cpo = C / G_out;
+  for (int i = threadIdx.x; i < 2 * G_out; i += blockDim.x) {
+    const int g = i >> 1, m = i & 1;
+    float s = 0.f;
+    for (int j = 0; j < cpo; ++j) s += tot[m * C + g * cpo + j];
+    stat_add(stats_out + ((size_t)b * G_out + g) * 2 + m, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupNorm apply (+affine) fused with SiLU / time-embedding add / residual add, optional statistics
 // of the result for a following GroupNorm.  Reference: Conv3DBlock.forward + ResBlock3D.forward
@@ -60,14 +109,14 @@ __device__ __forceinline__ uint4 f_to_h8(const float* f) {
 // Grid: (blocks, B); block = C8*R threads, each thread owns 8 fixed channels and strides over rows.
 // ------------------------------------------------------------------------------------------------
 template <int U, int MODE, bool STATS>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half* out_, const float* __restrict__ stats_in,
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half* out_, const stat_t* __restrict__ stats_in,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ temb, int temb_stride, const int* __restrict__ temb_step,
                                 long long temb_step_stride, const __half* res_, long long S, int C, int G, float eps,
-                                float* stats_out, int G_out) {
+                                stat_t* stats_out, int G_out) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];  // [2*C] when stats_out
+  extern __shared__ float sm[];  // [(R + 1)][2][C] when stats_out
   const int C8 = C >> 3;
   const int R = blockDim.x / C8;
   const int cv = threadIdx.x % C8;
@@ -75,25 +124,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half*
   const int b = blockIdx.y;
   const int c0 = cv * 8;
   const int cpg = C / G;
-  const float inv_n = 1.0f / ((float)S * (float)cpg);
 
   // sampler graphs read the time-embedding projections of ALL steps from one table, indexed by the device step counter
   const long long toff = (MODE == 0 && temb_step) ? (long long)(*temb_step) * temb_step_stride : 0;
   float sc[8], sh[8], ta[8];
+  gn_scale_shift(stats_in, gamma, beta, b, G, cpg, 1.0 / ((double)S * (double)cpg), eps, c0, sc, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    const int g = c / cpg;
-    const float s = stats_in[((size_t)b * G + g) * 2];
-    const float ss = stats_in[((size_t)b * G + g) * 2 + 1];
-    const float mean = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float ga = gamma[c];
-    sc[j] = ga * rstd;
-    sh[j] = beta[c] - mean * ga * rstd;
-    ta[j] = (MODE == 0 && temb) ? temb[toff + (size_t)b * temb_stride + c] : 0.f;
-  }
+  for (int j = 0; j < 8; ++j) ta[j] = (MODE == 0 && temb) ? temb[toff + (size_t)b * temb_stride + c0 + j] : 0.f;
   float as[8], ass[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) as[j] = ass[j] = 0.f;
@@ -151,31 +188,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half*
       }
     }
   }
-  if (STATS) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[c0 + j], as[j]);
-      atomicAdd(&sm[C + c0 + j], ass[j]);
-    }
-    __syncthreads();
-    const int cpo = C / G_out;
-    for (int g = threadIdx.x; g < G_out; g += blockDim.x) {
-      float s = 0.f, ss = 0.f;
-      for (int j = 0; j < cpo; ++j) {
-        s += sm[g * cpo + j];
-        ss += sm[C + g * cpo + j];
-      }
-      atomicAdd(&stats_out[((size_t)b * G_out + g) * 2], s);
-      atomicAdd(&stats_out[((size_t)b * G_out + g) * 2 + 1], ss);
-    }
-  }
+  if (STATS) block_stats_out(as, ass, sm, C, R, cv, rr, b, G_out, stats_out);
 }
 
-void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const float* gamma, const float* beta,
+void launch_gn_apply(const __half* y, __half* out, const stat_t* stats_in, const float* gamma, const float* beta,
                      const float* temb, int temb_stride, const __half* res, int B, long long S, int C, int G,
-                     float eps, int mode, float* stats_out, int G_out, cudaStream_t st, const int* temb_step,
+                     float eps, int mode, stat_t* stats_out, int G_out, cudaStream_t st, const int* temb_step,
                      long long temb_step_stride) {
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
@@ -189,7 +207,7 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
   long long cap = (148LL * per_sm + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  const size_t smem = stats_out ? 2 * C * sizeof(float) : 0;
+  const size_t smem = stats_out ? (size_t)(R + 1) * 2 * C * sizeof(float) : 0;
 #define GN_LAUNCH(UU, MM, SS)                                                                                     \
   launch_k(gn_apply_kernel<UU, MM, SS>, dim3(dim3(blocks, B)), dim3(threads), smem, st, y, out, stats_in, gamma, beta, temb, temb_stride, \
            temb_step, temb_step_stride, res, S, C, G, eps, stats_out, G_out)
@@ -210,16 +228,18 @@ void launch_gn_apply(const __half* y, __half* out, const float* stats_in, const 
 #undef GN_LAUNCH
 }
 
-// Split-K epilogue (see conv_igemm.cuh): y = fp16(ws + bias), per-(sample, group) statistics of the fp32 sums, and the
-// workspace is handed back zeroed for the next split-K convolution of the program.
-__global__ void splitk_finalize_kernel(float* ws_, const float* __restrict__ bias, __half* out_, float* stats,
-                                       long long S, int C, int G) {
+// Split-K epilogue (see conv_igemm.cuh): y = fp16(sum of the k-split slabs in index order + bias), and the
+// per-(sample, group) statistics of the fp32 sums.  Deterministic: no atomics on the data path.
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws_, long long slab, int nsplit,
+                                       const float* __restrict__ bias, __half* out_, stat_t* stats, long long S, int C,
+                                       int G) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int C8 = C >> 3, R = blockDim.x / C8, cv = threadIdx.x % C8, rr = threadIdx.x / C8, b = blockIdx.y;
-  float4* ws = reinterpret_cast<float4*>(ws_ + (size_t)b * S * C);
+  const float4* ws = reinterpret_cast<const float4*>(ws_ + (size_t)b * S * C);
   uint4* out = reinterpret_cast<uint4*>(out_ + (size_t)b * S * C);
+  const size_t slab4 = (size_t)slab / 4;
   float bs[8], as[8], ass[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -228,9 +248,12 @@ __global__ void splitk_finalize_kernel(float* ws_, const float* __restrict__ bia
   }
   for (long long row = (long long)blockIdx.x * R + rr; row < S; row += (long long)gridDim.x * R) {
     const size_t idx = (size_t)row * C8 + cv;
-    const float4 a0 = ws[idx * 2], a1 = ws[idx * 2 + 1];
-    ws[idx * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ws[idx * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a0 = ws[idx * 2], a1 = ws[idx * 2 + 1];
+    for (int k = 1; k < nsplit; ++k) {
+      const float4 b0 = ws[k * slab4 + idx * 2], b1 = ws[k * slab4 + idx * 2 + 1];
+      a0.x += b0.x, a0.y += b0.y, a0.z += b0.z, a0.w += b0.w;
+      a1.x += b1.x, a1.y += b1.y, a1.z += b1.z, a1.w += b1.w;
+    }
     float f[8] = {a0.x + bs[0], a0.y + bs[1], a0.z + bs[2], a0.w + bs[3],
                   a1.x + bs[4], a1.y + bs[5], a1.z + bs[6], a1.w + bs[7]};
     out[idx] = f_to_h8(f);
@@ -240,40 +263,22 @@ __global__ void splitk_finalize_kernel(float* ws_, const float* __restrict__ bia
       ass[j] += f[j] * f[j];
     }
   }
-  if (!stats) return;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[cv * 8 + j], as[j]);
-    atomicAdd(&sm[C + cv * 8 + j], ass[j]);
-  }
-  __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int j = 0; j < cpg; ++j) {
-      s += sm[g * cpg + j];
-      ss += sm[C + g * cpg + j];
-    }
-    atomicAdd(&stats[((size_t)b * G + g) * 2], s);
-    atomicAdd(&stats[((size_t)b * G + g) * 2 + 1], ss);
-  }
+  if (stats) block_stats_out(as, ass, sm, C, R, cv, rr, b, G, stats);
 }
-void launch_splitk_finalize(float* ws, const float* bias, __half* out, float* stats, int B, long long S, int C, int G,
-                            cudaStream_t st) {
+void launch_splitk_finalize(const float* ws, long long slab, int nsplit, const float* bias, __half* out, stat_t* stats,
+                            int B, long long S, int C, int G, cudaStream_t st) {
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
   long long want = (S + R - 1) / R;
   long long cap = (148LL * 4 + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  launch_k(splitk_finalize_kernel, dim3(blocks, B), dim3(C8 * R), 2 * C * sizeof(float), st, ws, bias, out, stats, S, C,
-           G);
+  launch_k(splitk_finalize_kernel, dim3(blocks, B), dim3(C8 * R), (size_t)(R + 1) * 2 * C * sizeof(float), st, ws, slab,
+           nsplit, bias, out, stats, S, C, G);
 }
 
 // Stand-alone statistics pass (used when the producer is not one of our conv / apply kernels, and by tests).
-__global__ void gn_stats_kernel(const __half* __restrict__ x_, long long S, int C, int G, float* stats) {
+__global__ void gn_stats_kernel(const __half* __restrict__ x_, long long S, int C, int G, stat_t* stats) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -291,34 +296,18 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x_, long long S, int 
       ass[j] += f[j] * f[j];
     }
   }
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[cv * 8 + j], as[j]);
-    atomicAdd(&sm[C + cv * 8 + j], ass[j]);
-  }
-  __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int j = 0; j < cpg; ++j) {
-      s += sm[g * cpg + j];
-      ss += sm[C + g * cpg + j];
-    }
-    atomicAdd(&stats[((size_t)b * G + g) * 2], s);
-    atomicAdd(&stats[((size_t)b * G + g) * 2 + 1], ss);
-  }
+  block_stats_out(as, ass, sm, C, R, cv, rr, b, G, stats);
 }
 
-void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* stats, cudaStream_t st) {
+void launch_gn_stats(const __half* x, int B, long long S, int C, int G, stat_t* stats, cudaStream_t st) {
   const int C8 = C / 8;
   const int R = C8 >= 256 ? 1 : 256 / C8;
   long long want = (S + R - 1) / R;
   long long cap = (148LL * 8 + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  launch_k(gn_stats_kernel, dim3(dim3(blocks, B)), dim3(C8 * R), 2 * C * sizeof(float), st, x, S, C, G, stats);
+  launch_k(gn_stats_kernel, dim3(dim3(blocks, B)), dim3(C8 * R), (size_t)(R + 1) * 2 * C * sizeof(float), st, x, S, C,
+           G, stats);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,7 +320,7 @@ void launch_gn_stats(const __half* x, int B, long long S, int C, int G, float* s
 // ------------------------------------------------------------------------------------------------
 // one block per (sample, spatial position); thread = (8-channel vector, depth split): the T slices are shared
 // among blockDim/C8 thread groups (was one thread per column walking all T slices: latency-bound at 1.5 TB/s)
-__global__ void attn_tsum_kernel(const __half* __restrict__ x_, const float* __restrict__ stats,
+__global__ void attn_tsum_kernel(const __half* __restrict__ x_, const stat_t* __restrict__ stats,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, __half* s_, int T,
                                  int P, int C, int G, float eps) {
   pdl_trigger();
@@ -361,21 +350,14 @@ __global__ void attn_tsum_kernel(const __half* __restrict__ x_, const float* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += sm[k * C + cv * 8 + j];
   const int cpg = C / G;
-  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
-  float o[8];
+  float sc[8], sh[8], o[8];
+  gn_scale_shift(stats, gamma, beta, b, G, cpg, 1.0 / ((double)T * (double)P * (double)cpg), eps, cv * 8, sc, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    const int g = c / cpg;
-    const float s = stats[((size_t)b * G + g) * 2], ss = stats[((size_t)b * G + g) * 2 + 1];
-    const float mean = s * inv_n;
-    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
-    o[j] = gamma[c] * rstd * (acc[j] - (float)T * mean) + (float)T * beta[c];
-  }
+  for (int j = 0; j < 8; ++j) o[j] = fmaf(sc[j], acc[j], (float)T * sh[j]);  // sum_t (sc*x + sh)
   reinterpret_cast<uint4*>(s_)[((size_t)b * P + p) * C8 + cv] = f_to_h8(o);
 }
 
-void launch_attn_tsum(const __half* x, const float* stats, const float* gamma, const float* beta, __half* s, int B,
+void launch_attn_tsum(const __half* x, const stat_t* stats, const float* gamma, const float* beta, __half* s, int B,
                       int T, int P, int C, int G, float eps, cudaStream_t st) {
   const int C8 = C / 8;
   int TS = 256 / C8;
@@ -424,13 +406,13 @@ void launch_add_bcast_t(__half* x, const __half* y, int B, int T, int P, int C, 
 // ------------------------------------------------------------------------------------------------
 template <int U>
 __global__ void __launch_bounds__(256) gn_res_tsum_kernel(__half* y_, const __half* res_,
-                                                          const float* __restrict__ stats_in,
+                                                          const stat_t* __restrict__ stats_in,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          int T, int P, int C, int G, float eps, float* stats_out,
+                                                          int T, int P, int C, int G, float eps, stat_t* stats_out,
                                                           int G_out, float* tsum) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];  // [2*C]
+  extern __shared__ float sm[];  // [(PB + 1)][2][C]
   const int C8 = C >> 3;
   const int PB = blockDim.x / C8;
   const int cv = threadIdx.x % C8, pp = threadIdx.x / C8;
@@ -438,21 +420,10 @@ __global__ void __launch_bounds__(256) gn_res_tsum_kernel(__half* y_, const __ha
   const int p = blockIdx.x * PB + pp;
   const int t0 = (int)((long long)ts * T / TS), t1 = (int)((long long)(ts + 1) * T / TS);
   const int cpg = C / G;
-  const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
   float sc[8], sh[8], acc[8], acc2[8];
+  gn_scale_shift(stats_in, gamma, beta, b, G, cpg, 1.0 / ((double)T * (double)P * (double)cpg), eps, cv * 8, sc, sh);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cv * 8 + j;
-    const int g = c / cpg;
-    const float s = stats_in[((size_t)b * G + g) * 2];
-    const float ss = stats_in[((size_t)b * G + g) * 2 + 1];
-    const float mean = s * inv_n;
-    const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
-    const float ga = gamma[c];
-    sc[j] = ga * rstd;
-    sh[j] = beta[c] - mean * ga * rstd;
-    acc[j] = acc2[j] = 0.f;
-  }
+  for (int j = 0; j < 8; ++j) acc[j] = acc2[j] = 0.f;
   if (p < P && pp < PB) {
     const size_t tstride = (size_t)P * C8;
     const size_t base = ((size_t)b * T * P + p) * C8 + cv;
@@ -493,26 +464,7 @@ __global__ void __launch_bounds__(256) gn_res_tsum_kernel(__half* y_, const __ha
     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  if (pp < PB) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[cv * 8 + j], acc[j]);
-      atomicAdd(&sm[C + cv * 8 + j], acc2[j]);
-    }
-  }
-  __syncthreads();
-  const int cpo = C / G_out;
-  for (int g = threadIdx.x; g < G_out; g += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    for (int j = 0; j < cpo; ++j) {
-      s += sm[g * cpo + j];
-      ss += sm[C + g * cpo + j];
-    }
-    atomicAdd(&stats_out[((size_t)b * G_out + g) * 2], s);
-    atomicAdd(&stats_out[((size_t)b * G_out + g) * 2 + 1], ss);
-  }
+  block_stats_out(acc, acc2, sm, C, PB, cv, pp, b, G_out, stats_out);  // threads beyond P contribute zeros
 }
 
 // depth splits so that about two waves of CTAs cover (B, P): the small levels have too few positions otherwise
@@ -525,13 +477,13 @@ int attn_tsum_splits(int B, int T, int P, int C) {
   return TS;
 }
 
-void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, const float* gamma, const float* beta,
-                        int B, int T, int P, int C, int G, float eps, float* stats_out, int G_out, float* tsum, int TS,
+void launch_gn_res_tsum(__half* y, const __half* res, const stat_t* stats_in, const float* gamma, const float* beta,
+                        int B, int T, int P, int C, int G, float eps, stat_t* stats_out, int G_out, float* tsum, int TS,
                         cudaStream_t st) {
   const int C8 = C / 8;
   const int PB = 256 / C8;
   const dim3 grid((P + PB - 1) / PB, TS, B);
-  launch_k(gn_res_tsum_kernel<4>, grid, dim3(C8 * PB), 2 * C * sizeof(float), st, y, res, stats_in, gamma, beta, T, P,
+  launch_k(gn_res_tsum_kernel<4>, grid, dim3(C8 * PB), (size_t)(PB + 1) * 2 * C * sizeof(float), st, y, res, stats_in, gamma, beta, T, P,
            C, G, eps, stats_out, G_out, tsum);
 }
 
@@ -542,7 +494,7 @@ void launch_gn_res_tsum(__half* y, const __half* res, const float* stats_in, con
 // whole matrix in every CTA: 74 MB of same-address L2 traffic per launch, ~40 us).
 constexpr int AG_P = 32, AG_N = 64, AG_K = 64, AG_T = 128;
 template <int TS>
-__global__ void __launch_bounds__(AG_T) attn_gemm_kernel(const float* __restrict__ tsum, const float* __restrict__ stats,
+__global__ void __launch_bounds__(AG_T) attn_gemm_kernel(const float* __restrict__ tsum, const stat_t* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const __half* __restrict__ Wt,  // [c][co] = Wpv[co][c]
                                                          const float* __restrict__ bias, __half* g_, int T, int P, int C,
@@ -597,12 +549,11 @@ __global__ void __launch_bounds__(AG_T) attn_gemm_kernel(const float* __restrict
   fetch(0);
   {
     const int cpg = C / G;
-    const float inv_n = 1.0f / ((float)T * (float)P * (float)cpg);
+    const double inv_n = 1.0 / ((double)T * (double)P * (double)cpg);
     for (int c = tid; c < C; c += AG_T) {
       const int gi = c / cpg;
-      const float su = stats[((size_t)b * G + gi) * 2], ss = stats[((size_t)b * G + gi) * 2 + 1];
-      const float mean = su * inv_n;
-      const float rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+      float mean, rstd;
+      stat_mean_rstd(stats + ((size_t)b * G + gi) * 2, inv_n, eps, mean, rstd);
       const float scl = gamma[c] * rstd;
       s_scl[c] = scl;
       s_shf[c] = (float)T * (beta[c] - mean * scl);
@@ -654,7 +605,7 @@ __global__ void __launch_bounds__(AG_T) attn_gemm_kernel(const float* __restrict
 bool attn_fused_supported(int C) { return C % 64 == 0 && C >= 64 && C / 8 <= 256; }
 
 // the attention itself: g = Wpv * GN(sum_t x) + bias (attn_gemm), then x[b,t,p,:] += g[b,p,:] (add_bcast_t)
-void launch_attn_proj_add(__half* x, const float* tsum, int TS, const float* stats, const float* gamma,
+void launch_attn_proj_add(__half* x, const float* tsum, int TS, const stat_t* stats, const float* gamma,
                           const float* beta, const __half* Wt, const float* bias, __half* g_ws, int B, int T, int P,
                           int C, int G, float eps, cudaStream_t st) {
   const dim3 grid((P + AG_P - 1) / AG_P, C / AG_N, B);
@@ -752,12 +703,19 @@ __device__ __forceinline__ float nan_guard(float x, int* flag) {
   return x;
 }
 
-__global__ void ddim_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise,
-                                   const float* __restrict__ coef_table, const int* __restrict__ step_ptr,
+// Loop state of a sampler graph lives on the device (SamplerCtl, ew_kernels.h): the step index that selects the
+// coefficient row / time-embedding row, the NaN flag, and where this step's noise comes from.
+__device__ __forceinline__ const float* ctl_noise(const SamplerCtl* ctl, int step, long long n) {
+  return ctl->noise ? ctl->noise + (long long)(step - ctl->noise_first) * n : nullptr;
+}
+
+__global__ void ddim_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise_imm,
+                                   const float* __restrict__ coef_table, const SamplerCtl* __restrict__ ctl,
                                    int step_imm, long long n, int* nan_flag) {
   pdl_trigger();
   pdl_wait();
-  const int step = step_ptr ? *step_ptr : step_imm;
+  const int step = ctl ? ctl->step : step_imm;
+  const float* noise = ctl ? ctl_noise(ctl, step, n) : noise_imm;
   const float* c = coef_table + (size_t)step * 8;
   const float c1 = c[0], c2 = c[1], c3 = c[2], c4 = c[3], sigma = c[4];
   int flag = 0;
@@ -773,36 +731,206 @@ __global__ void ddim_update_kernel(float* z, const float* __restrict__ eps, cons
   if (flag && nan_flag) atomicOr(nan_flag, 1);
 }
 
-__global__ void ddpm_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise, Coef8 c,
-                                   long long n) {
-  pdl_trigger();
-  pdl_wait();
-  const float s1m = c.v[0], sa = c.v[1], k1 = c.v[2], k2 = c.v[3], nz = c.v[4], sd = c.v[5];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float zt = z[i];
-    float z0 = __fdiv_rn(__fsub_rn(zt, __fmul_rn(s1m, eps[i])), sa);
-    z0 = fminf(fmaxf(z0, -1.0f), 1.0f);
-    const float mean = __fadd_rn(__fmul_rn(k1, z0), __fmul_rn(k2, zt));
-    z[i] = __fadd_rn(mean, __fmul_rn(__fmul_rn(nz, sd), noise[i]));
+// Philox4x32-10 (Salmon et al., SC'11; the counter-based generator behind cuRAND / torch CUDA): counter
+// (c0..c3), key (k0, k1) -> four 32-bit words.  Used for the DDPM ancestral noise when the caller passes none.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+// four N(0,1) draws for elements 4q..4q+3 of loop step `step`: counter (q lo, q hi, step, 0), key = seed;
+// u = (word + 0.5) / 2^32 in (0,1), Box-Muller on the pairs (0,1) and (2,3)
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, int step, unsigned long long q, float (&nz)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)r[2 * h] + 0.5f) * 2.3283064365386963e-10f;
+    const float u2 = ((float)r[2 * h + 1] + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.0f * logf(fminf(u1, 0.99999994f)));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    nz[2 * h] = rad * cs;
+    nz[2 * h + 1] = rad * sn;
   }
 }
 
-__global__ void advance_step_kernel(int* step) {
+// DDPM ancestral update (reference models/diffusion.py:287-338), one thread per 4 consecutive elements
+__device__ __forceinline__ float ddpm_one(float zt, float e, float nz, float s1m, float sa, float k1, float k2, float nzc,
+                                          float sd) {
+  float z0 = __fdiv_rn(__fsub_rn(zt, __fmul_rn(s1m, e)), sa);
+  z0 = fminf(fmaxf(z0, -1.0f), 1.0f);
+  const float mean = __fadd_rn(__fmul_rn(k1, z0), __fmul_rn(k2, zt));
+  return __fadd_rn(mean, __fmul_rn(__fmul_rn(nzc, sd), nz));
+}
+__global__ void ddpm_update_kernel(float* z, const float* __restrict__ eps, const float* __restrict__ noise_imm,
+                                   const float* __restrict__ coef_table, const SamplerCtl* __restrict__ ctl, Coef8 cimm,
+                                   long long n) {
   pdl_trigger();
-  pdl_wait(); *step += 1; }
+  pdl_wait();
+  const int step = ctl ? ctl->step : 0;
+  const float* c = ctl ? coef_table + (size_t)step * 8 : cimm.v;
+  const float s1m = c[0], sa = c[1], k1 = c[2], k2 = c[3], nzc = c[4], sd = c[5];
+  const float* noise = ctl ? ctl_noise(ctl, step, n) : noise_imm;
+  const unsigned long long seed = ctl ? ctl->seed : 0ull;
+  const long long nq = (n + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    float nz[4];
+    if (!noise) philox_normal4(seed, step, (unsigned long long)q, nz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = q * 4 + j;
+      if (i < n) z[i] = ddpm_one(z[i], eps[i], noise ? noise[i] : nz[j], s1m, sa, k1, k2, nzc, sd);
+    }
+  }
+}
+// raw generator output (tests: compared with the numpy restatement in oracle/philox.py)
+__global__ void philox_fill_kernel(float* out, unsigned long long seed, int step, long long n) {
+  const long long nq = (n + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    float nz[4];
+    philox_normal4(seed, step, (unsigned long long)q, nz);
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = nz[j];
+  }
+}
+void launch_philox_fill(float* out, unsigned long long seed, int step, long long n, cudaStream_t st) {
+  int blocks = cdiv((n + 3) / 4, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(philox_fill_kernel, dim3(blocks), dim3(256), 0, st, out, seed, step, n);
+}
 
-void launch_ddim_update(float* z, const float* eps, const float* noise, const float* coef_table, const int* step_ptr,
+__global__ void advance_step_kernel(SamplerCtl* ctl) {
+  pdl_trigger();
+  pdl_wait();
+  ctl->step += 1;
+}
+
+void launch_ddim_update(float* z, const float* eps, const float* noise, const float* coef_table, const SamplerCtl* ctl,
                         int step_imm, long long n, int* nan_flag, cudaStream_t st) {
   int blocks = cdiv(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(ddim_update_kernel, dim3(blocks), dim3(256), 0, st, z, eps, noise, coef_table, step_ptr, step_imm, n, nan_flag);
+  launch_k(ddim_update_kernel, dim3(blocks), dim3(256), 0, st, z, eps, noise, coef_table, ctl, step_imm, n, nan_flag);
 }
-void launch_ddpm_update(float* z, const float* eps, const float* noise, const Coef8& coef, long long n,
-                        cudaStream_t st) {
-  int blocks = cdiv(n, 256);
+void launch_ddpm_update(float* z, const float* eps, const float* noise, const float* coef_table, const SamplerCtl* ctl,
+                        const Coef8& coef, long long n, cudaStream_t st) {
+  int blocks = cdiv((n + 3) / 4, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(ddpm_update_kernel, dim3(blocks), dim3(256), 0, st, z, eps, noise, coef, n);
+  launch_k(ddpm_update_kernel, dim3(blocks), dim3(256), 0, st, z, eps, noise, coef_table, ctl, coef, n);
 }
+
+// The reference's NaN/Inf checkpoints of generate() (models/model.py:262-340): nan_to_num(nan=0, posinf=1, neginf=-1)
+// when anything is non-finite.  Applied per element unconditionally (identical on finite data), recorded in *flag.
+//   mode 0: only NaN -> 0 (the input check, :261-263);  mode 1: NaN -> 0, +inf -> 1, -inf -> -1
+__global__ void guard_kernel(float* x, long long n, int mode, int* flag) {
+  pdl_trigger();
+  pdl_wait();
+  int f = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (isnan(v)) {
+      x[i] = 0.f;
+      f = 1;
+    } else if (mode == 1 && isinf(v)) {
+      x[i] = v > 0 ? 1.f : -1.f;
+      f = 1;
+    }
+  }
+  if (f && flag) atomicOr(flag, 1);
+}
+__global__ void or_flag_kernel(int* dst, const int* src) { *dst |= *src; }
+void launch_or_flag(int* dst, const int* src, cudaStream_t st) { launch_k(or_flag_kernel, dim3(1), dim3(1), 0, st, dst, src); }
+void launch_guard(float* x, long long n, int mode, int* flag, cudaStream_t st) {
+  int blocks = cdiv(n, 1024);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  launch_k(guard_kernel, dim3(blocks), dim3(256), 0, st, x, n, mode, flag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training forward (reference models/diffusion.py:81-190), forward only:
+//   q_sample : z_t = sqrt_ac[t_b] * z_0 + sqrt_1m_ac[t_b] * noise          (per-sample timestep, fp32, reference op order)
+//   eps_mse  : per sample, sum of mask * (eps_pred - noise)^2 and sum of mask (mask (B, C, T) broadcast over H, W, or
+//              null); the Min-SNR-5 weighting and the batch mean are B-element host math in the mirror.
+// eps_mse is a two-stage, fixed-order reduction (per-block partials, then one block folds them): deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void q_sample_kernel(const float* __restrict__ z0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
+                                const float* __restrict__ sqrt_1m_ac, float* zt, long long per_sample) {
+  const int b = blockIdx.y;
+  const float a = sqrt_ac[t[b]], s = sqrt_1m_ac[t[b]];
+  const size_t base = (size_t)b * per_sample;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x)
+    zt[base + i] = __fadd_rn(__fmul_rn(a, z0[base + i]), __fmul_rn(s, noise[base + i]));
+}
+void launch_q_sample(const float* z0, const float* noise, const long long* t, const float* sqrt_ac,
+                     const float* sqrt_1m_ac, float* zt, int B, long long per_sample, cudaStream_t st) {
+  int blocks = cdiv(per_sample, 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  launch_k(q_sample_kernel, dim3(blocks, B), dim3(256), 0, st, z0, noise, t, sqrt_ac, sqrt_1m_ac, zt, per_sample);
+}
+
+constexpr int MSE_BLOCKS = 128;
+__global__ void __launch_bounds__(256) eps_mse_partial_kernel(const float* __restrict__ pred,
+                                                              const float* __restrict__ noise,
+                                                              const float* __restrict__ mask, long long per_sample,
+                                                              long long HW, double* partial /*[B][MSE_BLOCKS][2]*/) {
+  __shared__ double sh[2][256];
+  const int b = blockIdx.y;
+  const size_t base = (size_t)b * per_sample;
+  double se = 0.0, sm = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float m = mask ? mask[(size_t)b * (per_sample / HW) + i / HW] : 1.0f;
+    const float d = __fsub_rn(pred[base + i], noise[base + i]);
+    se += (double)__fmul_rn(__fmul_rn(d, d), m);
+    sm += (double)m;
+  }
+  sh[0][threadIdx.x] = se;
+  sh[1][threadIdx.x] = sm;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {  // fixed tree
+    if ((int)threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2] = sh[0][0];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * 2 + 1] = sh[1][0];
+  }
+}
+__global__ void eps_mse_final_kernel(const double* __restrict__ partial, int nblk, float* out /*[B][2]*/) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double se = 0.0, sm = 0.0;
+    for (int k = 0; k < nblk; ++k) {
+      se += partial[((size_t)b * nblk + k) * 2];
+      sm += partial[((size_t)b * nblk + k) * 2 + 1];
+    }
+    out[b * 2] = (float)se;
+    out[b * 2 + 1] = (float)sm;
+  }
+}
+size_t eps_mse_ws_bytes(int B) { return (size_t)B * MSE_BLOCKS * 2 * sizeof(double); }
+void launch_eps_mse(const float* pred, const float* noise, const float* mask, int B, long long per_sample, long long HW,
+                    double* ws, float* out, cudaStream_t st) {
+  launch_k(eps_mse_partial_kernel, dim3(MSE_BLOCKS, B), dim3(256), 0, st, pred, noise, mask, per_sample, HW, ws);
+  launch_k(eps_mse_final_kernel, dim3(B), dim3(32), 0, st, (const double*)ws, MSE_BLOCKS, out);
+}
+
 __global__ void zero_kernel(float* p, long long n) {
   pdl_trigger();
   pdl_wait();
@@ -813,7 +941,7 @@ void launch_zero(float* p, long long n, cudaStream_t st) {
   if (blocks > 148) blocks = 148;
   launch_k(zero_kernel, dim3(blocks), dim3(256), 0, st, p, n);
 }
-void launch_advance_step(int* step, cudaStream_t st) { launch_k(advance_step_kernel, dim3(1), dim3(1), 0, st, step); }
+void launch_advance_step(SamplerCtl* ctl, cudaStream_t st) { launch_k(advance_step_kernel, dim3(1), dim3(1), 0, st, ctl); }
 
 // t_dev[b] = t_table[*step] (sampler graphs) or an immediate value (step-wise DDPM)
 __global__ void set_t_kernel(long long* t_dev, const long long* __restrict__ t_table, const int* __restrict__ step,

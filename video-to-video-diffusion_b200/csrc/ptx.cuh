@@ -239,6 +239,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();  // true when B2V_PDL is set (off by default, see ew_kernels.cu)
+// first failed launch of the calling thread since the last take_launch_error() (cudaLaunchKernelEx status; a later
+// successful launch would otherwise overwrite what cudaGetLastError reports)
+void note_launch_error(cudaError_t e);
+cudaError_t take_launch_error();
 
 // launch with a (2,1,1) thread-block cluster (CTA pairs); grid.x must be even
 template <typename... KArgs, typename... Args>
@@ -257,7 +261,8 @@ inline void launch_k_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) note_launch_error(e);
 }
 
 template <typename... KArgs, typename... Args>
@@ -272,7 +277,8 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) note_launch_error(e);
 }
 
 // ---------------------------------------------------------------- operand-precision study (B2V_OPERANDS=bf16)
@@ -289,6 +295,28 @@ __device__ __forceinline__ float operand_round(float x) {
     return __uint_as_float(u & 0xFFFF0000u);
   }
   return x;
+}
+#endif
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// Per-(sample, group) (sum, sum of squares) are accumulated across CTAs as 64-bit FIXED-POINT integers (Q43.20):
+// integer addition is associative, so the result does not depend on the order in which CTAs arrive -- every
+// run of the same input is bitwise identical (fp32 atomics differed by ~1e-7 run to run, which fp16 storage
+// amplified to ~1e-3 over the depth of the network).  Each CTA's own partial is an fp32 sum built in a fixed order.
+typedef long long stat_t;
+#ifdef __CUDACC__
+__device__ __forceinline__ void stat_add(stat_t* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * 1048576.0f));
+}
+// mean and 1/sqrt(var + eps) of one group from its raw sums over n elements (inv_n = 1/n); the subtraction
+// E[x^2] - mean^2 is carried out in fp64 on the exact integer sums
+__device__ __forceinline__ void stat_mean_rstd(const stat_t* __restrict__ p, double inv_n, float eps, float& mean,
+                                               float& rstd) {
+  const double m = (double)p[0] * (1.0 / 1048576.0) * inv_n;
+  double var = (double)p[1] * (1.0 / 1048576.0) * inv_n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = rsqrtf((float)var + eps);
 }
 #endif
 

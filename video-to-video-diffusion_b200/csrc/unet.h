@@ -32,15 +32,19 @@ struct UProgram {
   DeviceStore ds;
   Pool pool;
   std::vector<Op> core;
-  Program fwd, ddim;
+  Program fwd, ddim, ddpm;  // one U-Net evaluation | + DDIM update + advance | + DDPM update + advance
   float *x_in = nullptr, *c_in = nullptr, *eps = nullptr;
   long long *t_dev = nullptr, *t_table = nullptr;
-  int *step_dev = nullptr, *nan_dev = nullptr;
-  float *coef_table = nullptr, *stats = nullptr, *silu_temb = nullptr, *proj = nullptr;
+  SamplerCtl* ctl = nullptr;  // device loop state of the sampler graphs (step counter, NaN flag, noise source)
+  int *step_dev = nullptr, *nan_dev = nullptr;  // = &ctl->step, &ctl->nan_flag
+  int loop_pos = 0, loop_n = 0;                  // host mirror of ctl->step / loop length of the running sampler
+  float *coef_table = nullptr, *silu_temb = nullptr, *proj = nullptr;
+  stat_t* stats = nullptr;
   size_t stats_cap = 0;
   TembSource temb;            // set before every run: per-sample table (forward) or all-steps table (DDIM graph)
   float *silu_all = nullptr, *proj_all = nullptr;  // time embedding of every DDIM step, computed once per sample() call
   int all_cap = 0;
+  long long stamp = 0;  // last use (least-recently-used program is evicted when the cache is full)
   int desc_rows = 0;  // rows of one time-embedding projection table (= UNet::proj_rows)
 };
 
@@ -60,6 +64,7 @@ struct UNet {
   std::map<std::string, std::unique_ptr<UProgram>> progs;
   UProgram* last = nullptr;
   UProgram* active = nullptr;
+  long long clock = 0;
 
   int finalize();
   UProgram* program(int B, int T, int h, int w);
@@ -70,6 +75,12 @@ struct UNet {
                   const long long* timesteps, int n, const float* ac, int n_train, float eta, const float* noise,
                   int* nan_flag, cudaStream_t st);
   int ddpm_step(long long t, const float* coef, const float* noise, cudaStream_t st);
+  // loop steps [first, first + count) of an n-step ancestral loop (step s handles timestep n-1-s)
+  int ddpm_run(const float* coef, int n, int first, int count, const float* noise, unsigned long long seed,
+               cudaStream_t st);
+  int ddpm_sample(const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w, const float* coef,
+                  int n, const float* noise, unsigned long long seed, cudaStream_t st);
+  int temb_tables(UProgram* up, int n, cudaStream_t st);  // time embedding of every loop step from up->t_table
   int sampler_end(float* z_out, cudaStream_t st);
   ~UNet();
 };

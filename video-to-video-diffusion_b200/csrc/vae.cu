@@ -94,7 +94,7 @@ struct VBuild {
   VBuild(VProgram& p) : b(p.prog.ops, p.pool, p.B, p.stats, p.stats_cap) { b.ds = &p.ds; }
   // conv -> GN(8) -> SiLU ; consumes x
   Act block(const std::string& name, const VBlockW& w, Act& x) {
-    float* s = b.new_stats(8);
+    stat_t* s = b.new_stats(8);
     Act y = b.conv(name + ".conv", w.conv, x, nullptr, s, 8);
     b.free(x);
     b.gn_apply(name + ".gn_silu", y, s, w.norm, -1, nullptr, 0, nullptr, 0);
@@ -102,10 +102,10 @@ struct VBuild {
   }
   // models/vae.py:50-56 ; consumes x
   Act res(const std::string& name, const VResW& r, Act& x) {
-    float* s1 = b.new_stats(8);
+    stat_t* s1 = b.new_stats(8);
     Act y1 = b.conv(name + ".conv1", r.conv1, x, nullptr, s1, 8);
     b.gn_apply(name + ".gn1_silu", y1, s1, r.n1, -1, nullptr, 0, nullptr, 0);
-    float* s2 = b.new_stats(8);
+    stat_t* s2 = b.new_stats(8);
     Act y2 = b.conv(name + ".conv2", r.conv2, y1, nullptr, s2, 8);
     b.free(y1);
     b.gn_apply(name + ".gn2_res_silu", y2, s2, r.n2, -1, &x, 1, nullptr, 0);
@@ -117,7 +117,7 @@ struct VBuild {
 static int build_vae_program(VAE& v, VProgram& vp, int which) {
   const int B = vp.B, T = vp.T, H = vp.H, W = vp.W, L = v.desc.latent_dim, Cin = v.desc.in_channels;
   vp.stats_cap = (size_t)B * 16 * 64;
-  vp.stats = (float*)vp.ds.alloc(vp.stats_cap * sizeof(float));
+  vp.stats = (stat_t*)vp.ds.alloc(vp.stats_cap * sizeof(stat_t));
   if (which == 0) {
     if (H % 4 || W % 4) return fail("vae.encode: H and W must be multiples of 4");
     vp.in_numel = (long long)B * Cin * T * H * W;
@@ -132,8 +132,8 @@ static int build_vae_program(VAE& v, VProgram& vp, int which) {
   VBuild vb(vp);
   Builder& b = vb.b;
   {
-    float* stats = vp.stats;
-    const size_t bytes = vp.stats_cap * sizeof(float);
+    float* stats = reinterpret_cast<float*>(vp.stats);
+    const size_t bytes = vp.stats_cap * sizeof(stat_t);
     Op op;
     op.name = "zero_stats";
     op.run = [=](cudaStream_t st) { launch_zero(stats, (long long)(bytes / sizeof(float)), st); };

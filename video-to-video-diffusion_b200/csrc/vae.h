@@ -20,7 +20,8 @@ struct VProgram {
   DeviceStore ds;
   Pool pool;
   Program prog;
-  float *in = nullptr, *out = nullptr, *stats = nullptr;
+  float *in = nullptr, *out = nullptr;
+  stat_t* stats = nullptr;
   size_t stats_cap = 0;
 };
 

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib, ops
+from ..models._native import check_sampler_args
 
 logger = logging.getLogger(__name__)
 
@@ -92,12 +93,14 @@ class DDIMSampler(_Stitching):
     def sample(self, shape, conditioning, num_inference_steps, device, eta=0.0, progress=True):
         ts = np.ascontiguousarray(self._get_timesteps(num_inference_steps), dtype=np.int64)
         n = len(ts)
-        dev = torch.device(device)
-        z = torch.randn(shape, device=dev)
-        cond = conditioning.detach().to(dev, torch.float32).contiguous()
         acp = self.diffusion.alphas_cumprod.detach().float().cpu().contiguous()
         if not _is_native(self.model):
-            return self._sample_generic(z, cond, ts, acp, eta)
+            dev = torch.device(device)
+            z = torch.randn(shape, device=dev)
+            return self._sample_generic(z, conditioning.detach().to(dev, torch.float32).contiguous(), ts, acp, eta)
+        shape, dev = check_sampler_args(self.model, shape, conditioning, device)  # ValueError before any C call
+        z = torch.randn(shape, device=dev)
+        cond = conditioning.detach().to(dev, torch.float32).contiguous()
         B, _, T, h, w = shape
         if z.numel() == 0:
             return z

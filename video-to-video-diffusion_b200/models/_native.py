@@ -7,7 +7,38 @@ from .. import _lib
 
 
 def _weights_version(module):
-    return sum(p._version for p in module.parameters()) + sum(b._version for b in module.buffers())
+    """identity + in-place version + storage address of every parameter / buffer: changes when a tensor is replaced
+    (load_state_dict(assign=True), `p.data = ...`, .to()), updated in place (optimiser step, copy_) or re-allocated.
+    In-place writes through `.data` / raw pointers bypass torch's version counter: call `invalidate_native()` then."""
+    return tuple((id(t), t._version, t.data_ptr()) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def normalize_device(device):
+    """torch.device with an explicit index ('cuda' -> the current device), so equality means 'same GPU'"""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def check_sampler_args(model, shape, cond, device):
+    """Shape / dtype / device contract of the native sampler entry points.  The C ABI copies B*latent_dim*T*h*w floats
+    computed from `shape` and the model's latent_dim, so a conditioning tensor of another shape would be read out of
+    bounds; the reference fails in torch.cat for the same inputs (models/unet3d.py:372) -- this raises ValueError."""
+    shape = tuple(int(s) for s in shape)
+    if len(shape) != 5:
+        raise ValueError(f"sampler: shape must be (B, C, T, h, w), got {shape}")
+    if shape[1] != model.latent_dim:
+        raise ValueError(f"sampler: shape[1] = {shape[1]} does not match the U-Net's latent_dim = {model.latent_dim}")
+    if tuple(cond.shape) != shape:
+        raise ValueError(f"sampler: conditioning has shape {tuple(cond.shape)}, expected {shape} "
+                         "(was the conditioning latent depth-upsampled to the target depth?)")
+    dev = normalize_device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"sampler: device {dev} -- this implementation runs on B200 only (no CPU fallback)")
+    if not cond.is_floating_point():
+        raise TypeError(f"sampler: conditioning must be a floating-point tensor, got {cond.dtype}")
+    return shape, dev
 
 
 class NativeHandle:
@@ -21,6 +52,7 @@ class NativeHandle:
         self.device = None
 
     def get(self, module, desc, device):
+        device = normalize_device(device)
         ver = _weights_version(module)
         if self.handle is not None and self.version == ver and self.device == device:
             return self.handle
@@ -43,6 +75,10 @@ class NativeHandle:
 
     def __getstate__(self):
         return {"kind": self.kind, "handle": None, "version": None, "device": None}
+
+    def invalidate(self):
+        """force a rebuild on next use (after weight changes torch cannot see, e.g. writes through `.data`)"""
+        self.version = None
 
     def close(self):
         if self.handle is not None:

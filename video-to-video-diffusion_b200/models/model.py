@@ -4,11 +4,14 @@ the reference does (including reading the U-Net keys from the top level of the d
 encode -> depth upsample -> DDIM/DDPM -> decode entirely on libb2v.so.  Training (`forward`, `save_checkpoint`)
 is out of scope of this package.
 """
+import ctypes
+
+import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
-from .diffusion import GaussianDiffusion
+from .. import _lib, ops
+from .diffusion import GaussianDiffusion, ddpm_noise_budget_bytes
 from .unet3d import UNet3D
 from .vae import VideoVAE
 
@@ -75,22 +78,62 @@ class VideoToVideoDiffusion(nn.Module):
         if sampler not in ("ddpm", "ddim"):
             raise ValueError(f"Unknown sampler: {sampler}")
         device = v_in.device
+        B, C, T_in, H, W = v_in.shape
+        T_out = int(target_depth) if target_depth is not None else T_in
         if v_in.numel() == 0:  # empty batch
-            B, C, T_in, H, W = v_in.shape
-            return torch.empty((B, C, target_depth or T_in, H, W), dtype=torch.float32, device=device)
-        v_in = torch.nan_to_num(v_in.float(), nan=0.0, posinf=float("inf"), neginf=float("-inf"))
-        z_in = _guard(self.vae.encode(v_in))
-        if target_depth is not None:
-            cond = _guard(ops.upsample_depth(z_in, int(target_depth)))
-        else:
-            cond = z_in
-        shape = tuple(cond.shape)
-        torch.randn(shape, device=device)  # the reference draws (and discards) this tensor: keeps the RNG aligned
-        if sampler == "ddpm":
-            z0 = self.diffusion.p_sample_loop(self.unet, shape, cond, device, progress=True)
-        else:
+            return torch.empty((B, C, T_out, H, W), dtype=torch.float32, device=device)
+        if not v_in.is_cuda:
+            raise RuntimeError(f"generate: input is on {device}; this implementation runs on B200 only (no CPU fallback)")
+        if C != self.vae.in_channels or H % 4 or W % 4:
+            raise ValueError(f"generate: v_in {tuple(v_in.shape)} needs {self.vae.in_channels} channels and H, W % 4 == 0")
+        v_in = v_in.detach().float().contiguous()
+        shape = (B, self.vae.latent_dim, T_out, H // 4, W // 4)
+        n_lat = int(np.prod(shape))
+        n = self.diffusion.timesteps
+        if sampler == "ddpm" and n * n_lat * 4 > ddpm_noise_budget_bytes():
+            return self._generate_staged(v_in, shape, target_depth)  # per-step noise does not fit: chunked loop
+        # RNG order of the reference: a discarded randn(latent_shape) (models/model.py:303), the sampler's initial
+        # draw, then (DDPM) one randn_like per step
+        torch.randn(shape, device=device)
+        z_init = torch.randn(shape, device=device)
+        cfg = _lib.SamplerCfg()
+        keep = []  # host tables must outlive the call
+        if sampler == "ddim":
             from ..inference.sampler import DDIMSampler
-            z0 = DDIMSampler(self.diffusion, self.unet).sample(shape, cond, num_inference_steps, device)
+            ts = np.ascontiguousarray(DDIMSampler(self.diffusion, self.unet)._get_timesteps(num_inference_steps),
+                                      dtype=np.int64)
+            acp = self.diffusion.alphas_cumprod.detach().float().cpu().contiguous()
+            keep += [ts, acp]
+            cfg.sampler, cfg.n, cfg.n_train, cfg.eta = 0, len(ts), acp.numel(), 0.0
+            cfg.timesteps = ts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+            cfg.alphas_cumprod = ctypes.cast(acp.data_ptr(), ctypes.POINTER(ctypes.c_float))
+        else:
+            rows = self.diffusion.ddpm_coefficients()
+            noise = torch.empty((n,) + shape, dtype=torch.float32, device=device)
+            for s in range(n):
+                noise[s] = torch.randn_like(z_init)
+            keep += [rows, noise]
+            cfg.sampler, cfg.n = 1, n
+            cfg.ddpm_coef = ctypes.cast(rows.data_ptr(), ctypes.POINTER(ctypes.c_float))
+            cfg.noise = noise.data_ptr()
+        out = torch.empty((B, C, T_out, H, W), dtype=torch.float32, device=device)
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().b2v_generate(self.unet.native(device), self.vae.native(device), ctypes.byref(cfg),
+                                               _lib.dptr(v_in), _lib.dptr(z_init), _lib.dptr(out), B, T_in, T_out, H, W,
+                                               _lib.dptr(flag, torch.int32), _lib.stream()), "generate")
+        self.last_nan_flag = flag  # device tensor: .item() it to learn whether one of the reference's NaN guards fired
+        return out
+
+    def _generate_staged(self, v_in, shape, target_depth):
+        """generate() as separate C calls (encode / upsample / chunked DDPM loop / decode) for the case where the
+        reference-ordered per-step noise of a DDPM run exceeds the staging budget"""
+        device = v_in.device
+        v_in = torch.nan_to_num(v_in, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+        z_in = _guard(self.vae.encode(v_in))
+        cond = _guard(ops.upsample_depth(z_in, int(target_depth))) if target_depth is not None else z_in
+        torch.randn(shape, device=device)
+        z0 = self.diffusion.p_sample_loop(self.unet, shape, cond, device, progress=True)
         return _guard(self.vae.decode(_guard(z0)))
 
     def count_parameters(self):

@@ -81,6 +81,14 @@ class UNet3D(nn.Module):
         self.num_levels, self.use_checkpoint = len(channel_mult), use_checkpoint
         self.num_heads, self.time_embed_dim = num_heads, time_embed_dim
         nl = self.num_levels
+        # limits of the B200 kernels (DESIGN.md "known limits"), raised here rather than at the first forward
+        if model_channels % 64:
+            raise ValueError(f"UNet3D: model_channels = {model_channels} must be a multiple of 64 (64-channel K chunks "
+                             "of the implicit-GEMM convolution)")
+        if 2 * latent_dim * 3 > 64:
+            raise ValueError(f"UNet3D: latent_dim = {latent_dim} too large for the packed conv_in (<= 10)")
+        if not 1 <= nl <= 8 or num_res_blocks < 1:
+            raise ValueError("UNet3D: 1..8 levels and at least one ResBlock per level")
 
         def stage(cin, cout, attn):
             layers = [ResBlock3D(cin, cout, time_embed_dim)]
@@ -129,7 +137,11 @@ class UNet3D(nn.Module):
 
     def native(self, device):
         """the b2v_unet handle holding this module's current weights on `device`"""
-        return self._native.get(self, self._desc(), torch.device(device))
+        return self._native.get(self, self._desc(), device)
+
+    def invalidate_native(self):
+        """call after changing weights in a way torch's version counters cannot see (writes through `.data`)"""
+        self._native.invalidate()
 
     @torch.no_grad()
     def forward(self, x, t, c):

@@ -79,6 +79,11 @@ class SliceInterpolationVAE(nn.Module):
     def __init__(self, in_channels=3, latent_dim=4, base_channels=64, scaling_factor=0.18215,
                  gradient_checkpointing=False):
         super().__init__()
+        # limits of the B200 kernels (DESIGN.md "known limits"), raised here rather than at the first encode / decode
+        if base_channels % 64:
+            raise ValueError(f"SliceInterpolationVAE: base_channels = {base_channels} must be a multiple of 64")
+        if latent_dim > 16 or in_channels > 16:
+            raise ValueError("SliceInterpolationVAE: latent_dim and in_channels must be <= 16 (narrow-head kernels)")
         self.latent_dim, self.in_channels = latent_dim, in_channels
         self.base_channels = base_channels
         self.gradient_checkpointing = gradient_checkpointing
@@ -93,7 +98,10 @@ class SliceInterpolationVAE(nn.Module):
             self._native.close()
             self._native_scale = float(self.scaling_factor)
         d = _lib.VAEDesc(self.in_channels, self.latent_dim, self.base_channels, float(self.scaling_factor))
-        return self._native.get(self, d, torch.device(device))
+        return self._native.get(self, d, device)
+
+    def invalidate_native(self):
+        self._native.invalidate()
 
     @torch.no_grad()
     def encode(self, x):

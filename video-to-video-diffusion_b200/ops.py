@@ -6,6 +6,17 @@ import torch
 from . import _lib
 
 KIND_K3, KIND_K1, KIND_DOWN, KIND_UPT = 0, 1, 2, 3
+STAT_SCALE = float(1 << 20)  # GroupNorm statistics cross the C ABI as int64 Q43.20 fixed point (include/b2v.h)
+
+
+def stats_to_float(stats):
+    """int64 (B, G, 2) fixed-point (sum, sumsq) -> float64"""
+    return stats.to(torch.float64) / STAT_SCALE
+
+
+def stats_from_float(stats):
+    """(B, G, 2) floating (sum, sumsq) -> the int64 fixed-point form the kernels read"""
+    return torch.round(stats.to(torch.float64) * STAT_SCALE).to(torch.int64).contiguous()
 
 
 def to_cl16(x, cpad=None):
@@ -48,10 +59,11 @@ class Conv:
             out = torch.empty((B, self.cout, D, oH, oW), dtype=torch.float32, device=x0.device)
         else:
             out = torch.empty((B, D, oH, oW, self.cout), dtype=torch.float16, device=x0.device)
-        stats = torch.zeros((B, groups, 2), dtype=torch.float32, device=x0.device) if groups else None
+        stats = torch.zeros((B, groups, 2), dtype=torch.int64, device=x0.device) if groups else None
         _lib.check(_lib.lib().b2v_conv_forward(
             self._h, _lib.dptr(x0, torch.float16), _lib.dptr(x1, torch.float16),
-            _lib.dptr(out, torch.float32 if out_fp32 else torch.float16), int(out_fp32), _lib.dptr(stats), groups,
+            _lib.dptr(out, torch.float32 if out_fp32 else torch.float16), int(out_fp32), _lib.dptr(stats, torch.int64),
+            groups,
             int(tanh), B, D, H, W, _lib.stream()), "conv_forward")
         return out, stats
 
@@ -68,11 +80,11 @@ def gn_apply(y, stats, gamma, beta, groups, temb=None, res=None, mode=0, groups_
     """y: cl16 (B,D,H,W,C).  mode 0: silu(gn(y)) + temb ; mode 1: silu(gn(y) + res).  Returns (out, stats_out)."""
     B, D, H, W, C = y.shape
     out = torch.empty_like(y)
-    so = torch.zeros((B, groups_out, 2), dtype=torch.float32, device=y.device) if groups_out else None
+    so = torch.zeros((B, groups_out, 2), dtype=torch.int64, device=y.device) if groups_out else None
     _lib.check(_lib.lib().b2v_gn_apply(
-        _lib.dptr(y, torch.float16), _lib.dptr(out, torch.float16), _lib.dptr(stats), _lib.dptr(gamma), _lib.dptr(beta),
-        _lib.dptr(temb), _lib.dptr(res, torch.float16), B, D * H * W, C, groups, mode, _lib.dptr(so), groups_out,
-        _lib.stream()), "gn_apply")
+        _lib.dptr(y, torch.float16), _lib.dptr(out, torch.float16), _lib.dptr(stats, torch.int64), _lib.dptr(gamma),
+        _lib.dptr(beta), _lib.dptr(temb), _lib.dptr(res, torch.float16), B, D * H * W, C, groups, mode,
+        _lib.dptr(so, torch.int64), groups_out, _lib.stream()), "gn_apply")
     return out, so
 
 
@@ -82,19 +94,19 @@ def res_attn_tail(y, res, stats_in, gamma2, beta2, groups2, gamma_a, beta_a, gro
     B, D, H, W, C = y.shape
     out = y.clone()
     wt = wpv.t().contiguous().to(torch.float16)
-    sm = torch.zeros((B, groups_a, 2), dtype=torch.float32, device=y.device)
+    sm = torch.zeros((B, groups_a, 2), dtype=torch.int64, device=y.device)
     ws = torch.empty(B * 5 * H * W * C, dtype=torch.float32, device=y.device)
     _lib.check(_lib.lib().b2v_res_attn_tail(
-        _lib.dptr(out, torch.float16), _lib.dptr(res, torch.float16), _lib.dptr(stats_in), _lib.dptr(gamma2),
+        _lib.dptr(out, torch.float16), _lib.dptr(res, torch.float16), _lib.dptr(stats_in, torch.int64), _lib.dptr(gamma2),
         _lib.dptr(beta2), groups2, _lib.dptr(gamma_a), _lib.dptr(beta_a), groups_a, _lib.dptr(wt, torch.float16),
-        _lib.dptr(bias), _lib.dptr(sm), _lib.dptr(ws), ws.numel(), B, D, H * W, C, _lib.stream()), "res_attn_tail")
+        _lib.dptr(bias), _lib.dptr(sm, torch.int64), _lib.dptr(ws), ws.numel(), B, D, H * W, C, _lib.stream()), "res_attn_tail")
     return out
 
 
 def gn_stats(x, groups):
     B, D, H, W, C = x.shape
-    st = torch.zeros((B, groups, 2), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().b2v_gn_stats(_lib.dptr(x, torch.float16), B, D * H * W, C, groups, _lib.dptr(st),
+    st = torch.zeros((B, groups, 2), dtype=torch.int64, device=x.device)
+    _lib.check(_lib.lib().b2v_gn_stats(_lib.dptr(x, torch.float16), B, D * H * W, C, groups, _lib.dptr(st, torch.int64),
                                        _lib.stream()), "gn_stats")
     return st
 
@@ -139,3 +151,36 @@ def stitch_normalize(acc, wsum):
     _lib.check(_lib.lib().b2v_stitch_normalize(_lib.dptr(acc), _lib.dptr(wsum), acc.numel(), _lib.stream()),
                "stitch_normalize")
     return acc
+
+
+def philox_normal(n, seed, step, device):
+    """the N(0,1) draws b2v_ddpm_sample generates on the device for loop step `step` when no noise is supplied"""
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().b2v_philox_normal(_lib.dptr(out), int(seed), int(step), n, _lib.stream()), "philox_normal")
+    return out
+
+
+def q_sample(z0, t, noise, sqrt_ac, sqrt_1m_ac):
+    """forward diffusion z_t = sqrt_ac[t] z_0 + sqrt_1m_ac[t] noise (reference models/diffusion.py:81-107)"""
+    B = z0.shape[0]
+    zt = torch.empty_like(z0)
+    if z0.numel():
+        _lib.check(_lib.lib().b2v_q_sample(_lib.dptr(z0), _lib.dptr(noise), _lib.dptr(t, torch.int64), _lib.dptr(sqrt_ac),
+                                           _lib.dptr(sqrt_1m_ac), _lib.dptr(zt), B, z0.numel() // B, _lib.stream()),
+                   "q_sample")
+    return zt
+
+
+def eps_mse(eps_pred, noise, mask=None):
+    """per sample (sum mask*(eps_pred-noise)^2, sum mask) -> (B, 2) fp32; mask (B, C, T) or None"""
+    B, C, T, H, W = eps_pred.shape
+    out = torch.zeros((B, 2), dtype=torch.float32, device=eps_pred.device)
+    if eps_pred.numel() == 0:
+        return out
+    L = _lib.lib()
+    ws = torch.empty(int(L.b2v_eps_mse_ws_bytes(B)) // 8, dtype=torch.float64, device=eps_pred.device)
+    _lib.check(L.b2v_eps_mse(_lib.dptr(eps_pred), _lib.dptr(noise), _lib.dptr(mask), _lib.dptr(out),
+                             _lib.dptr(ws, torch.float64), ws.numel() * 8, B, C * T * H * W, H * W, _lib.stream()),
+               "eps_mse")
+    return out
