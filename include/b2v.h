@@ -212,6 +212,9 @@ int b2v_res_attn_tail(void* y, const void* res, const int64_t* stats_in, const f
 /* DDIM update of one step, coef = device fp32[8] {c1,c2,c3,c4,sigma,..} (inference/sampler.py:299-329) */
 int b2v_ddim_update(float* z, const float* eps, const float* noise, const float* coef, long long n, int* nan_flag,
                     void* stream);
+/* DDPM ancestral update of one step (models/diffusion.py:287-338), in place on z; coef = HOST fp32[8] as in
+ * b2v_ddpm_step; noise = DEVICE fp32 [n] (this step's torch.randn_like draw)                                   */
+int b2v_ddpm_update(float* z, const float* eps, const float* noise, const float* coef, long long n, void* stream);
 
 #ifdef __cplusplus
 }

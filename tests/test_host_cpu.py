@@ -153,3 +153,64 @@ def test_gather_of_decoded_slabs_world2_gloo(ragged):
     import sys
     sys.path.insert(0, ROOT)
     mp.spawn(_gather_worker, args=(2, _free_port(), ragged), nprocs=2, join=True)
+
+
+def test_c_ddim_timesteps_matches_reference_subset():
+    """b2v_ddim_timesteps is host-only integer logic (inference/sampler.py:221-239): checked against the golden lists"""
+    from helpers import golden
+    from v2v_b200 import _lib
+    g = golden("schedule.pt")
+    L = _lib.lib()
+    buf = (ctypes.c_int64 * 64)()
+    for n, key in ((50, "ts50"), (20, "ts20"), (7, "ts7")):
+        cnt = L.b2v_ddim_timesteps(1000, n, buf, 64)
+        assert cnt == len(g[key]) and list(buf[:cnt]) == g[key].tolist()
+    assert L.b2v_ddim_timesteps(1000, 50, buf, 10) < 0 and "too small" in _lib.last_error()
+    assert L.b2v_ddim_timesteps(1000, 0, buf, 64) < 0
+
+
+def test_sampler_entry_points_validate_shapes_before_the_c_call():
+    """a conditioning tensor that was not depth-upsampled (or a wrong channel count) must raise like the
+    reference's torch.cat does, not reach the pointer-based C ABI"""
+    from helpers import tiny_unet
+    from v2v_b200.inference import DDIMSampler, DDPMSampler
+    from v2v_b200.models import GaussianDiffusion
+    m = tiny_unet()
+    d = GaussianDiffusion("cosine", 20)
+    shape = (1, 4, 6, 4, 4)
+    with pytest.raises(ValueError, match="conditioning has shape"):
+        DDIMSampler(d, m).sample(shape, torch.zeros(1, 4, 2, 4, 4), 5, "cuda")
+    with pytest.raises(ValueError, match="latent_dim"):
+        DDIMSampler(d, m).sample((1, 3, 6, 4, 4), torch.zeros(1, 3, 6, 4, 4), 5, "cuda")
+    with pytest.raises(ValueError, match="conditioning has shape"):
+        DDPMSampler(d, m).sample(shape, torch.zeros(2, 4, 6, 4, 4), "cuda")
+    with pytest.raises(ValueError):
+        d.p_sample_loop(m, (1, 4, 6, 4), torch.zeros(1, 4, 6, 4), "cuda")
+
+
+def test_unsupported_configs_fail_at_construction():
+    from v2v_b200.models import UNet3D, VideoVAE
+    with pytest.raises(ValueError, match="multiple of 64"):
+        UNet3D(latent_dim=4, model_channels=96)
+    with pytest.raises(ValueError, match="latent_dim"):
+        UNet3D(latent_dim=12, model_channels=64, channel_mult=(1,), attention_levels=[])
+    with pytest.raises(ValueError, match="multiple of 64"):
+        VideoVAE(1, 4, 32, 1.0)
+    UNet3D(latent_dim=4, model_channels=192, channel_mult=(1, 2), num_res_blocks=1, attention_levels=[1])  # 24 ch / group
+
+
+def test_native_handle_tracks_parameter_identity_and_versions():
+    """a sum of version counters misses replaced / re-assigned tensors"""
+    from helpers import tiny_unet
+    from v2v_b200.models._native import _weights_version, normalize_device
+    m = tiny_unet()
+    v0 = _weights_version(m)
+    with torch.no_grad():
+        m.conv_in.weight.add_(1.0)  # in-place update: version counter
+    v1 = _weights_version(m)
+    m.conv_in.weight = torch.nn.Parameter(m.conv_in.weight.detach().clone())  # replaced object, version 0 again
+    v2 = _weights_version(m)
+    m.conv_in.bias.data = m.conv_in.bias.data.clone()  # .data re-assignment: new storage
+    v3 = _weights_version(m)
+    assert len({v0, v1, v2, v3}) == 4
+    assert normalize_device("cpu") == torch.device("cpu")

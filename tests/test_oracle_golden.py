@@ -150,3 +150,20 @@ def test_benchmark_model_resolution_and_init_hash():
     assert m.count_parameters() == g["counts"]
     assert g["counts"]["unet"] == 264658184 and g["counts"]["vae"] == 90301593
     assert sd_hash(sd) == g["sd_hash"]
+
+
+def test_philox_restatement_against_random123_known_answers():
+    """the device generator of b2v_ddpm_sample (noise == NULL) is Philox4x32-10; the numpy restatement the GPU test
+    compares against is pinned here with Random123's published known-answer vectors (kat_vectors: philox4x32 10)"""
+    import numpy as np
+    from oracle import philox as P
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        got = P.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(v) for v in got] == list(out)
+    x = P.normal(400_000, 1234, 7)
+    assert abs(x.mean()) < 5e-3 and abs(x.std() - 1) < 5e-3 and np.isfinite(x).all()
+    assert not np.array_equal(P.normal(64, 1234, 7), P.normal(64, 1234, 8))  # the step is part of the counter

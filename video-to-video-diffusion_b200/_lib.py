@@ -89,6 +89,7 @@ SIGNATURES = {
                                   c_int, c_int, _P]),
     "b2v_gn_stats": (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, _P]),
     "b2v_ddim_update": (c_int, [_P, _P, _P, _P, c_longlong, _P, _P]),
+    "b2v_ddpm_update": (c_int, [_P, _P, _P, POINTER(c_float), c_longlong, _P]),
 }
 
 

@@ -409,6 +409,14 @@ int b2v_gn_stats(const void* x, int B, long long S, int C, int G, int64_t* stats
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
+int b2v_ddpm_update(float* z, const float* eps, const float* noise, const float* coef, long long n, void* stream) {
+  if (!z || !eps || !noise || !coef) return fail("ddpm_update: null argument");
+  Coef8 c8;
+  for (int i = 0; i < 8; ++i) c8.v[i] = coef[i];
+  launch_ddpm_update(z, eps, noise, nullptr, nullptr, c8, n, (cudaStream_t)stream);
+  g_launches += 1;
+  return check_launches("ddpm_update");
+}
 int b2v_ddim_update(float* z, const float* eps, const float* noise, const float* coef, long long n, int* nan_flag,
                     void* stream) {
   launch_ddim_update(z, eps, noise, coef, nullptr, 0, n, nan_flag, (cudaStream_t)stream);

@@ -39,3 +39,36 @@ def gather_slabs(local, counts=None, group=None):
     out = torch.empty((world * nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * nmax: r * nmax + counts[r]] for r in range(world)], dim=0)
+
+
+class SlabGatherer:
+    """The final gather of decoded slabs, taken off the critical path: every call issues one asynchronous
+    all_gather_into_tensor (NCCL's own stream, ordered after the producer by an event) into one of `depth` rotating
+    output buffers and returns immediately, so the next batch's encode / sampling overlaps the transfer and the ranks
+    are not re-synchronised once per batch (a per-batch blocking collective couples every step to the slowest,
+    power-capped GPU).  `finish()` waits for everything outstanding; buffers are reused, so consume a result before
+    `depth` further gathers are issued."""
+
+    def __init__(self, depth=2, group=None):
+        self.depth, self.group, self.bufs, self.pending, self.i = depth, group, {}, [], 0
+
+    def gather(self, local):
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return local
+        world = dist.get_world_size(self.group)
+        key = (tuple(local.shape), local.dtype, local.device)
+        if key not in self.bufs:
+            self.bufs[key] = [torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                                          device=local.device) for _ in range(self.depth)]
+        out = self.bufs[key][self.i % self.depth]
+        self.i += 1
+        while len(self.pending) >= self.depth:  # the buffer about to be overwritten must have been produced
+            self.pending.pop(0)[0].wait()
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=self.group, async_op=True)
+        self.pending.append((work, local))  # keep the source alive until the collective has read it
+        return out
+
+    def finish(self):
+        for work, _ in self.pending:
+            work.wait()
+        self.pending = []

@@ -119,6 +119,14 @@ def ddim_update(z, eps, coef, noise=None):
     return flag
 
 
+def ddpm_update(z, eps, noise, coef_row):
+    """in-place DDPM ancestral update of z (fp32); coef_row: 8 host floats (GaussianDiffusion.ddpm_coefficients()[t])"""
+    coef = (ctypes.c_float * 8)(*[float(v) for v in coef_row])
+    _lib.check(_lib.lib().b2v_ddpm_update(_lib.dptr(z), _lib.dptr(eps), _lib.dptr(noise), coef, z.numel(),
+                                          _lib.stream()), "ddpm_update")
+    return z
+
+
 def upsample_depth(z, depth):
     """F.interpolate(z, (depth, h, w), mode='trilinear', align_corners=False) for unchanged h, w"""
     B, C, D, H, W = z.shape
