@@ -108,8 +108,10 @@ __device__ __forceinline__ void block_stats_out(const float (&as)[8], const floa
 // stats_in : [B][G][2] raw (sum, sumsq) over S*cpg elements, produced by the conv epilogue.
 // Grid: (blocks, B); block = C8*R threads, each thread owns 8 fixed channels and strides over rows.
 // ------------------------------------------------------------------------------------------------
+// 3 CTAs of 256 threads per SM need <= 85 registers per thread (allocated in units of 8 -> 80): the launcher sizes the grid
+// as ONE resident wave, so a variant that silently drops to 2 CTAs per SM runs a ragged second wave (+33 %)
 template <int U, int MODE, bool STATS>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* y_, __half* out_, const stat_t* __restrict__ stats_in,
+__global__ void __launch_bounds__(256, (!STATS && U <= 4) ? 3 : 2) gn_apply_kernel(const __half* y_, __half* out_, const stat_t* __restrict__ stats_in,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ temb, int temb_stride, const int* __restrict__ temb_step,
                                 long long temb_step_stride, const __half* res_, long long S, int C, int G, float eps,
@@ -203,7 +205,9 @@ void launch_gn_apply(const __half* y, __half* out, const stat_t* stats_in, const
   // 3 CTAs per SM over the whole launch = one resident wave (72-80 registers x 256 threads): few long-lived CTAs
   // amortise the per-CTA prologue (statistics -> scale / shift) and leave no ragged last wave.  Measured against 8 per
   // SM: -12 % on the U-Net's GroupNorm-apply total, -3 % on the decoder's (B2V_GN_CTAS_PER_SM overrides for A/B runs).
-  static const int per_sm = getenv("B2V_GN_CTAS_PER_SM") ? atoi(getenv("B2V_GN_CTAS_PER_SM")) : 3;
+  static const int per_sm_env = getenv("B2V_GN_CTAS_PER_SM") ? atoi(getenv("B2V_GN_CTAS_PER_SM")) : 0;
+  // the statistics-producing variants hold 16 more accumulators and fit 2 CTAs per SM
+  const int per_sm = per_sm_env ? per_sm_env : ((stats_out || U > 4) ? 2 : 3);
   long long cap = (148LL * per_sm + B - 1) / B;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
