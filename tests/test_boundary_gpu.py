@@ -99,6 +99,32 @@ def test_generate_from_c_abi_calls_only(cuda_dev):
         L.b2v_vae_destroy(v)
 
 
+def test_generate_same_depth_ragged_batch_and_shape_errors(cuda_dev):
+    """generate() without a target depth (no upsample stage), batch 3, non-square 20 x 28 slices (partial TMA boxes in
+    every layer); shape contract errors surface as ValueError / RuntimeError before anything is launched"""
+    m, g = _tiny_model(cuda_dev)
+    gen = torch.Generator().manual_seed(71)
+    v = (torch.rand((3, 1, 5, 20, 28), generator=gen) * 2 - 1).to(cuda_dev)
+    torch.manual_seed(2)
+    got = m.generate(v, "ddim", 3)
+    assert got.shape == (3, 1, 5, 20, 28) and torch.isfinite(got).all() and m.last_nan_flag.item() == 0
+    torch.manual_seed(2)
+    with torch.no_grad():
+        ref = R.generate(_sd(m, cuda_dev), g["config"], v, "ddim", 3)
+    n = lambda a: (a.clamp(-1, 1) + 1) / 2  # noqa: E731
+    assert rel_l2(got, ref) < 0.2 and R.psnr(n(got), n(ref)) > 25.0, (rel_l2(got, ref), R.psnr(n(got), n(ref)))
+    torch.manual_seed(2)
+    assert torch.equal(m.generate(v, "ddim", 3), got)
+    with pytest.raises(ValueError):
+        m.generate(v[:, :, :, :18], "ddim", 3)  # H % 4 != 0
+    with pytest.raises(ValueError):
+        m.generate(v.expand(3, 2, 5, 20, 28).contiguous(), "ddim", 3)  # channel count
+    with pytest.raises(RuntimeError):
+        m.generate(v.cpu(), "ddim", 3)
+    with pytest.raises(ValueError):
+        m.generate(v, "euler")
+
+
 def test_ddpm_update_bit_exact_and_teacher_forced_step(cuda_dev):
     """the ancestral update reproduces the reference's eager fp32 chain bit for bit (models/diffusion.py:287-338), and
     one full DDPM step (U-Net + update) teacher-forced on the reference's z_t stays within the eps tolerance"""

@@ -147,6 +147,36 @@ def _gather_worker(rank, world, port, ragged):
         dist.destroy_process_group()
 
 
+def _async_gather_worker(rank, world, port):
+    import torch.distributed as dist
+    from v2v_b200.dist import SlabGatherer
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = SlabGatherer(depth=2)
+        outs = []
+        for step in range(5):  # more batches than buffers: results are consumed before their buffer is reused
+            local = torch.full((2, 1, 2, 3, 1), float(10 * step + rank))
+            out = g.gather(local)
+            outs.append((step, out))
+            if step % 2 == 1:
+                g.finish()
+                for st, o in outs:
+                    assert torch.equal(o[:2], torch.full((2, 1, 2, 3, 1), float(10 * st)))
+                    assert torch.equal(o[2:], torch.full((2, 1, 2, 3, 1), float(10 * st + 1)))
+                outs = []
+        g.finish()
+        assert not g.pending
+    finally:
+        dist.destroy_process_group()
+
+
+def test_async_slab_gatherer_world2_gloo():
+    """bench.py's N > 1 path: one asynchronous all-gather per batch into rotating buffers, completed by finish()"""
+    import sys
+    sys.path.insert(0, ROOT)
+    mp.spawn(_async_gather_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("ragged", [False, True])
 def test_gather_of_decoded_slabs_world2_gloo(ragged):
     """the N>1 data path: each rank decodes its shard, one all-gather rebuilds the single-GPU result"""

@@ -398,6 +398,72 @@ def test_config3_full_512_volume(cuda_dev, bench_model):
     assert abs(p_new - p_ref) <= 0.05
 
 
+@pytest.mark.timeout(900)
+def test_config4_ddpm_batch4_full_shape_short_schedule(cuda_dev):
+    """BASELINE config 4 (DDPM, batch 32 sharded over 8 GPUs = 4 patches per rank) at the per-rank shape
+    (4,8,48,48,48): the whole-loop C entry on a 4-step schedule against the fp32 oracle's ancestral loop fed the same
+    torch noise stream (the 1000-step loop is this step 1000 times; the update itself is bit-exact, see
+    test_ddpm_update_bit_exact_and_teacher_forced_step)."""
+    import os
+    import yaml
+    from v2v_b200.models import VideoToVideoDiffusion
+    cfg = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "golden", "slice_interpolation_full_medium.yaml")))
+    cfg = dict(cfg, diffusion_timesteps=4)
+    torch.manual_seed(0)
+    m = VideoToVideoDiffusion(cfg).eval().to(cuda_dev)
+    sd = _sd(m, cuda_dev)
+    _, unet_cfg, diff_cfg = R.resolve_config(cfg)
+    g = torch.Generator().manual_seed(44)
+    cond = torch.randn((4, 8, 48, 48, 48), generator=g).to(cuda_dev)
+    model = lambda z, t, c: R.unet_forward(sd, unet_cfg, z, t, c, "unet.")  # noqa: E731
+    torch.manual_seed(9)
+    with torch.no_grad():
+        ref = R.ddpm_sample(model, R.diffusion_buffers(**diff_cfg), tuple(cond.shape), cond, cuda_dev)
+    torch.manual_seed(9)
+    got = m.diffusion.p_sample_loop(m.unet, tuple(cond.shape), cond, cuda_dev, progress=False)
+    errs = [rel_l2(got[i], ref[i]) for i in range(4)]
+    print(f"config-4 shape, DDPM 4-step schedule, batch 4: per-sample rel-L2 {['%.2e' % e for e in errs]}")
+    assert max(errs) < 2e-2, errs
+    torch.manual_seed(9)
+    assert torch.equal(m.diffusion.p_sample_loop(m.unet, tuple(cond.shape), cond, cuda_dev, progress=False), got)
+
+
+@pytest.mark.timeout(1200)
+def test_config5_stitched_volume_vs_oracle(cuda_dev, bench_model):
+    """BASELINE config 5 in miniature at the real window shape: a (1,1,8,288,288) slab -> 2 x 2 windows of 192 x 192
+    (stride 96), each encode -> 8->48 depth upsample -> DDIM -> decode, Gaussian-blended -- generate_volume (windows
+    batched 4 at a time) against the oracle's per-window generate() + the reference's blend (inference/sampler.py:379-451)"""
+    from v2v_b200.inference.volume import generate_volume, window_starts
+    m, cfg = bench_model
+    sd = _sd(m, cuda_dev)
+    g = torch.Generator().manual_seed(55)
+    vol = (torch.rand((1, 1, 8, 288, 288), generator=g) * 2 - 1).to(cuda_dev)
+    starts = window_starts(8, 288, 288)
+    assert starts == [(0, 0, 0), (0, 0, 96), (0, 96, 0), (0, 96, 96)]
+    # the same initial noise for every window on both sides (the oracle runs windows one at a time, ours in one batch)
+    orig, cache = torch.randn, {}
+
+    def same_noise(shape, **k):
+        key = tuple(shape[1:])
+        if key not in cache:
+            cache[key] = orig((1,) + key, generator=torch.Generator().manual_seed(7)).to(cuda_dev)
+        return cache[key].expand(tuple(shape)).clone()
+
+    try:
+        torch.randn = same_noise
+        got = generate_volume(m, vol, "ddim", 2, batch=4)
+        with torch.no_grad():
+            patches = [R.generate(sd, cfg, vol[:, :, :, h0:h0 + 192, w0:w0 + 192].contiguous(), "ddim", 2, target_depth=48)
+                       for (_, h0, w0) in starts]
+    finally:
+        torch.randn = orig
+    ref = R.stitch(patches, [(0, h0, w0) for (_, h0, w0) in starts], (1, 1, 48, 288, 288))
+    n = lambda a: (a.clamp(-1, 1) + 1) / 2  # noqa: E731
+    err, p = rel_l2(got, ref), R.psnr(n(got), n(ref))
+    print(f"config-5 stitched (1,1,48,288,288): rel-L2 {err:.3e}, PSNR(new, ref) {p:.1f} dB")
+    assert got.shape == ref.shape and err < 5e-2 and p > 35.0, (err, p)
+
+
 def test_ragged_shapes_empty_batch_and_nan_input(cuda_dev):
     """edge cases: odd depth / non-square latent (partial TMA boxes everywhere), batch 3, empty batch, NaNs in v_in"""
     from v2v_b200.models import VideoToVideoDiffusion
