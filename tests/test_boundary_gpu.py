@@ -100,14 +100,14 @@ def test_generate_from_c_abi_calls_only(cuda_dev):
 
 
 def test_generate_same_depth_ragged_batch_and_shape_errors(cuda_dev):
-    """generate() without a target depth (no upsample stage), batch 3, non-square 20 x 28 slices (partial TMA boxes in
+    """generate() without a target depth (no upsample stage), batch 3, non-square 24 x 40 slices (partial TMA boxes in
     every layer); shape contract errors surface as ValueError / RuntimeError before anything is launched"""
     m, g = _tiny_model(cuda_dev)
     gen = torch.Generator().manual_seed(71)
-    v = (torch.rand((3, 1, 5, 20, 28), generator=gen) * 2 - 1).to(cuda_dev)
+    v = (torch.rand((3, 1, 5, 24, 40), generator=gen) * 2 - 1).to(cuda_dev)
     torch.manual_seed(2)
     got = m.generate(v, "ddim", 3)
-    assert got.shape == (3, 1, 5, 20, 28) and torch.isfinite(got).all() and m.last_nan_flag.item() == 0
+    assert got.shape == (3, 1, 5, 24, 40) and torch.isfinite(got).all() and m.last_nan_flag.item() == 0
     torch.manual_seed(2)
     with torch.no_grad():
         ref = R.generate(_sd(m, cuda_dev), g["config"], v, "ddim", 3)
@@ -118,7 +118,7 @@ def test_generate_same_depth_ragged_batch_and_shape_errors(cuda_dev):
     with pytest.raises(ValueError):
         m.generate(v[:, :, :, :18], "ddim", 3)  # H % 4 != 0
     with pytest.raises(ValueError):
-        m.generate(v.expand(3, 2, 5, 20, 28).contiguous(), "ddim", 3)  # channel count
+        m.generate(v.expand(3, 2, 5, 24, 40).contiguous(), "ddim", 3)  # channel count
     with pytest.raises(RuntimeError):
         m.generate(v.cpu(), "ddim", 3)
     with pytest.raises(ValueError):
