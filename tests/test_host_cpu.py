@@ -244,3 +244,22 @@ def test_native_handle_tracks_parameter_identity_and_versions():
     v3 = _weights_version(m)
     assert len({v0, v1, v2, v3}) == 4
     assert normalize_device("cpu") == torch.device("cpu")
+
+
+def test_header_is_valid_c_and_links_from_a_c_program(tmp_path):
+    """include/b2v.h compiles as strict C99 and a C program linked against libb2v.so can call the host-side entry
+    points (the boundary is a C ABI, not a C++ one)"""
+    import shutil
+    import subprocess
+    from v2v_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.lib()
+    exe = str(tmp_path / "host_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "host_check.c"), "-o", exe, "-L", libdir, "-l:libb2v.so",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "ok abi=2" in r.stdout
