@@ -160,7 +160,8 @@ int b2v_stitch_accumulate(const float* patch, float* acc, float* wsum, const flo
 int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* stream);
 
 /* utils/metrics.py:125-193  calculate_video_metrics: a, b (BC, T, H, W) fp32 in [0, max_val]; out: DEVICE fp32 [T][2]
- * = per depth slice (sum of squared error, sum of the 11x11 box-filter SSIM map) over all (bc, h, w)           */
+ * = per depth slice (sum of squared error, sum of the 11x11 box-filter SSIM map) over all (bc, h, w); per-tile partials
+ * are folded in a fixed order (deterministic); the scratch for them is a stream-ordered allocation on `stream`     */
 int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
                       void* stream);
 

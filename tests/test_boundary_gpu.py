@@ -125,6 +125,34 @@ def test_generate_same_depth_ragged_batch_and_shape_errors(cuda_dev):
         m.generate(v, "euler")
 
 
+def test_program_cache_evicts_least_recently_used_shape_only(cuda_dev):
+    """more input shapes than cached programs (6): the least recently used plan is dropped, the others keep their
+    captured graphs, and a re-planned shape reproduces its first result bit for bit (clear-all thrashing)"""
+    m = tiny_unet(0).to(cuda_dev)
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(1, 4, 2, 4, 4), (1, 4, 3, 4, 4), (2, 4, 2, 4, 6), (1, 4, 4, 8, 8), (1, 4, 2, 8, 4), (3, 4, 2, 4, 4),
+              (1, 4, 5, 6, 6), (2, 4, 3, 6, 4)]
+    data, first = [], []
+    for shp in shapes:
+        x, c = torch.randn(shp, generator=gen).to(cuda_dev), torch.randn(shp, generator=gen).to(cuda_dev)
+        t = torch.randint(0, 1000, (shp[0],), generator=gen).to(cuda_dev)
+        data.append((x, t, c))
+        first.append(m(x, t, c))
+    for i in (0, 7, 3, 1, 0):  # evicted and still-cached shapes alike
+        x, t, c = data[i]
+        assert torch.equal(m(x, t, c), first[i]), shapes[i]
+    # a sampler keeps working across evictions of other shapes
+    from v2v_b200.inference import DDIMSampler
+    from v2v_b200.models import GaussianDiffusion
+    diff = GaussianDiffusion("cosine", 1000).to(cuda_dev)
+    torch.manual_seed(1)
+    a = DDIMSampler(diff, m).sample(shapes[3], data[3][2], 3, cuda_dev, progress=False)
+    for i in (4, 5, 6, 7, 0, 1, 2):
+        m(*data[i])
+    torch.manual_seed(1)
+    assert torch.equal(DDIMSampler(diff, m).sample(shapes[3], data[3][2], 3, cuda_dev, progress=False), a)
+
+
 def test_ddpm_update_bit_exact_and_teacher_forced_step(cuda_dev):
     """the ancestral update reproduces the reference's eager fp32 chain bit for bit (models/diffusion.py:287-338), and
     one full DDPM step (U-Net + update) teacher-forced on the reference's z_t stays within the eps tolerance"""

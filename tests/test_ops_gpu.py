@@ -260,6 +260,7 @@ def test_video_metrics_kernel_matches_reference_definition(cuda_dev):
     a = torch.rand((2, 1, 5, 70, 45), generator=g).to(cuda_dev)
     b = (a + 0.05 * torch.randn((2, 1, 5, 70, 45), generator=g).to(cuda_dev)).clamp(0, 1)
     got, ref = calculate_video_metrics(a, b, max_val=1.0), R.video_metrics(a, b)
+    assert calculate_video_metrics(a, b, max_val=1.0) == got  # per-tile partials folded in a fixed order: same bits
     assert abs(got["psnr"] - ref["psnr"]) < 1e-3 and abs(got["ssim"] - ref["ssim"]) < 1e-4
     assert max(abs(x - y) for x, y in zip(got["psnr_per_frame"], ref["psnr_per_frame"])) < 1e-3
     assert max(abs(x - y) for x, y in zip(got["ssim_per_frame"], ref["ssim_per_frame"])) < 1e-4

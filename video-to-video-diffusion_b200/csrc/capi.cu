@@ -293,11 +293,14 @@ int b2v_stitch_normalize(float* acc, const float* wsum, long long n, void* strea
 int b2v_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
                        void* stream) {
   if (check_device()) return -1;
-  B2V_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * 2 * T, (cudaStream_t)stream));
-  launch_video_metrics(a, b, out, BC, T, H, W, max_val, (cudaStream_t)stream);
-  g_launches += 1;
-  B2V_CUDA(cudaGetLastError());
-  return 0;
+  if (BC <= 0 || T <= 0 || H <= 0 || W <= 0) return fail("video_metrics: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = nullptr;  // per-block partials, stream-ordered allocation: freed when the fold kernel has read them
+  B2V_CUDA(cudaMallocAsync(&ws, video_metrics_ws_bytes(BC, T, H, W), st));
+  launch_video_metrics(a, b, out, ws, BC, T, H, W, max_val, st);
+  g_launches += 2;
+  B2V_CUDA(cudaFreeAsync(ws, st));
+  return check_launches("video_metrics");
 }
 
 int b2v_extract_patch(const float* vol, float* out, int D, int H, int W, int z0, int z1, int y0, int x0, int pd, int ph,

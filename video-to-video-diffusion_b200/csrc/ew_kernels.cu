@@ -1188,7 +1188,7 @@ void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStr
 // the reference does two .item() host syncs per slice instead.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) video_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                            float* out, int T, int H, int W, float C1, float C2) {
+                                                            float* part, int T, int H, int W, float C1, float C2) {
   pdl_trigger();
   pdl_wait();
   constexpr int TS = 32, R = 5, IN = TS + 2 * R;  // 42
@@ -1254,17 +1254,33 @@ __global__ void __launch_bounds__(256) video_metrics_kernel(const float* __restr
     red[1][threadIdx.x >> 5] = ssim;
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
+  if (threadIdx.x < 2) {  // one partial per block (no atomics: the second pass folds them in a fixed order)
     float s = 0.f;
     for (int k = 0; k < 8; ++k) s += red[threadIdx.x][k];
-    atomicAdd(out + t * 2 + threadIdx.x, s);
+    (void)t;
+    part[(((size_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = s;
   }
 }
-void launch_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
-                          cudaStream_t st) {
+// out[t] = sum over (bc, tile) of the block partials of slice t, in index order (fp64 accumulation): deterministic
+__global__ void video_metrics_fold_kernel(const float* __restrict__ part, float* out, int BC, int T, int tiles) {
+  const int t = blockIdx.x, m = threadIdx.x;
+  if (m >= 2) return;
+  double s = 0.0;
+  for (int bc = 0; bc < BC; ++bc) {
+    const float* p = part + ((size_t)(bc * T + t) * tiles) * 2 + m;
+    for (int k = 0; k < tiles; ++k) s += (double)p[(size_t)k * 2];
+  }
+  out[t * 2 + m] = (float)s;
+}
+size_t video_metrics_ws_bytes(int BC, int T, int H, int W) {
+  return (size_t)BC * T * ((W + 31) / 32) * ((H + 31) / 32) * 2 * sizeof(float);
+}
+void launch_video_metrics(const float* a, const float* b, float* out, float* ws, int BC, int T, int H, int W,
+                          float max_val, cudaStream_t st) {
   const float C1 = (0.01f * max_val) * (0.01f * max_val), C2 = (0.03f * max_val) * (0.03f * max_val);
-  launch_k(video_metrics_kernel, dim3((W + 31) / 32, (H + 31) / 32, BC * T), dim3(256), 0, st, a, b, out, T, H, W, C1,
-           C2);
+  const dim3 grid((W + 31) / 32, (H + 31) / 32, BC * T);
+  launch_k(video_metrics_kernel, grid, dim3(256), 0, st, a, b, ws, T, H, W, C1, C2);
+  launch_k(video_metrics_fold_kernel, dim3(T), dim3(32), 0, st, (const float*)ws, out, BC, T, (int)(grid.x * grid.y));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -68,8 +68,9 @@ void launch_stitch_accumulate(const float* patch, float* acc, float* wsum, const
                               const float* gw, int BC, int pd, int ph, int pw, int D, int H, int W, int d0, int h0,
                               int w0, cudaStream_t st);
 void launch_stitch_normalize(float* acc, const float* wsum, long long n, cudaStream_t st);
-void launch_video_metrics(const float* a, const float* b, float* out, int BC, int T, int H, int W, float max_val,
-                          cudaStream_t st);
+size_t video_metrics_ws_bytes(int BC, int T, int H, int W);
+void launch_video_metrics(const float* a, const float* b, float* out, float* ws, int BC, int T, int H, int W,
+                          float max_val, cudaStream_t st);
 void launch_extract_patch(const float* vol, float* out, int H, int W, int z0, int n, int y0, int x0, int pd, int ph,
                           int pw, float lo, float hi, float a, float b, cudaStream_t st);
 void launch_nc32_to_cl16(const float* in, __half* out, int B, int C, int Cpad, long long S, cudaStream_t st);
