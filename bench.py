@@ -91,13 +91,15 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_run(evals, warm=0, threads=None):
+def cpu_reference_run(evals, warm=0, threads=None, budget_s=None, min_iters=None):
     """The reference's CPU path, restated (oracle/ref_port.py; /root/reference does not exist on the GPU box), fp32 on
     the host cores, run as the REAL pipeline of BASELINE configs[0] on one patch -- VAE encode of the thick patch,
     trilinear depth upsample, then the first `warm + evals` iterations of the actual DDIM-50 loop (timesteps 999, 980,
     ...: U-Net evaluation + scheduler update each, z carried from step to step), then the VAE decode of the latent to
     48 slices.  Everything is wall-clocked; with warm + evals >= 51 this IS config 1 in full.  A patch-volume costs
-    t_enc + 51 * mean(t_step over the `evals` timed iterations) + t_dec."""
+    t_enc + 51 * mean(t_step over the `evals` timed iterations) + t_dec.
+    budget_s: wall-clock guard for a full run on a slow host -- if, after 3 iterations, the projected total exceeds it,
+    the loop is cut to `min_iters` iterations and the remainder extrapolated (the line says which happened)."""
     import torch.nn.functional as F
     from oracle import ref_port as R
     from v2v_b200.models import VideoToVideoDiffusion
@@ -121,13 +123,19 @@ def cpu_reference_run(evals, warm=0, threads=None):
         t_enc = time.perf_counter() - t0
         torch.randn(tuple(cond.shape))
         z = torch.randn(tuple(cond.shape))
-        for i in range(n_run):
+        i = 0
+        while i < n_run:
             t0 = time.perf_counter()
             t = torch.full((1,), int(ts[i]), dtype=torch.long)
             eps = R.unet_forward(sd, unet_cfg, z, t, cond, "unet.")
             a_prev = acp[ts[i + 1]] if i < len(ts) - 1 else torch.tensor(1.0)
             z = R.ddim_step(z, eps, acp[ts[i]], a_prev)
             t_steps.append(time.perf_counter() - t0)
+            i += 1
+            if budget_s and i == 3 and min_iters and min_iters < n_run:
+                projected = t_enc + n_run * sum(t_steps[1:]) / 2 + 7.0 * t_enc  # the decode costs ~6-7x the encode
+                if projected > budget_s:
+                    n_run, warm = min_iters, max(0, min_iters - evals)
         t0 = time.perf_counter()
         out = R.vae_decode(sd, z, vae_cfg["scaling_factor"], "vae.")
         t_dec = time.perf_counter() - t0
@@ -143,7 +151,7 @@ def cpu_reference_run(evals, warm=0, threads=None):
                        f"slices {t_dec:.2f}s; patch-volume time = enc + 51*step + dec = {t_vol:.1f}s"
                        + (" (config 1 run in full, nothing extrapolated)" if full else " (loop extrapolated x51)")),
             "seconds_per_volume": t_vol, "timed_seconds": t_enc + sum(timed) + t_dec, "timed_iterations": len(timed),
-            "wall_seconds": t_enc + sum(t_steps) + t_dec}
+            "wall_seconds": t_enc + sum(t_steps) + t_dec, "warm_iterations": len(t_steps) - len(timed), "full": full}
 
 
 def cpu_baseline(threads=None):
@@ -211,7 +219,10 @@ def run_reference(args, rank):
         return
     steps = max(1, min(args.steps, DDIM_STEPS + 1))
     warm = max(0, args.warmup) if args.quick_reference else max(max(0, args.warmup), DDIM_STEPS + 1 - steps)
-    r = cpu_reference_run(steps, warm)
+    # a host too slow to finish config 1 within the budget (default 270 s) falls back to steps + warmup iterations
+    budget = float(os.environ.get("B2V_REF_BUDGET_S", "270"))
+    r = cpu_reference_run(steps, warm, budget_s=budget, min_iters=min(DDIM_STEPS + 1, steps + max(0, args.warmup)))
+    warm = r["warm_iterations"]
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["timed_iterations"], "warmup": warm,
             "ms_per_step": 1000.0 * r["timed_seconds"] / r["timed_iterations"], "higher_is_better": True,
@@ -220,7 +231,7 @@ def run_reference(args, rank):
                        "note": ("CPU path of the reference (oracle port) on the host cores, one patch at a time (CPU "
                                 "throughput does not depend on the batch); a step = one iteration of the real DDIM loop; "
                                 + ("value = 1 / (encode + all 51 iterations + decode) = BASELINE configs[0] run in full, "
-                                   "nothing extrapolated" if not args.quick_reference else
+                                   "nothing extrapolated" if r["full"] else
                                    "value = 1 / (encode + 51 * mean timed iteration + decode), loop extrapolated")),
                        "seconds_per_volume": r["seconds_per_volume"], "timed_seconds": r["timed_seconds"],
                        "wall_seconds": r["wall_seconds"]},
