@@ -74,33 +74,44 @@ int b2v_unet_create(b2v_unet** out, const b2v_unet_desc* d) {
 }
 void b2v_unet_destroy(b2v_unet* u) { delete u; }
 int b2v_unet_load_weight(b2v_unet* u, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!u) return fail("unet_load_weight: null handle");
   return store_weight(u->u.wm, u->u.finalized, key, data, shape, ndim);
 }
-int b2v_unet_finalize(b2v_unet* u) { return u->u.finalize(); }
+int b2v_unet_finalize(b2v_unet* u) {
+  if (!u) return fail("unet_finalize: null handle");
+  return u->u.finalize();
+}
 int b2v_unet_forward(b2v_unet* u, const float* x, const int64_t* t, const float* c, float* eps_out, int B, int T,
                      int h, int w, void* stream) {
+  if (!u) return fail("unet_forward: null handle");
   return u->u.forward(x, (const long long*)t, c, eps_out, B, T, h, w, (cudaStream_t)stream);
 }
 int b2v_ddim_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
                     const int64_t* timesteps, int n, const float* alphas_cumprod, int n_train, float eta,
                     const float* noise, int* nan_flag, void* stream) {
+  if (!u) return fail("ddim_sample: null handle");
   return u->u.ddim_sample(z_init, cond, z_out, B, T, h, w, (const long long*)timesteps, n, alphas_cumprod, n_train,
                           eta, noise, nan_flag, (cudaStream_t)stream);
 }
 int b2v_sampler_begin(b2v_unet* u, const float* z_init, const float* cond, int B, int T, int h, int w, void* stream) {
+  if (!u) return fail("sampler_begin: null handle");
   return u->u.sampler_begin(z_init, cond, B, T, h, w, (cudaStream_t)stream);
 }
 int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise, void* stream) {
+  if (!u) return fail("ddpm_step: null handle");
   return u->u.ddpm_step((long long)t, coef, noise, (cudaStream_t)stream);
 }
-int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) { return u->u.sampler_end(z_out, (cudaStream_t)stream); }
+int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) {
+  if (!u) return fail("sampler_end: null handle"); return u->u.sampler_end(z_out, (cudaStream_t)stream); }
 int b2v_ddpm_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
                     const float* coef, int n, const float* noise, uint64_t seed, void* stream) {
+  if (!u) return fail("ddpm_sample: null handle");
   return u->u.ddpm_sample(z_init, cond, z_out, B, T, h, w, coef, n, noise, (unsigned long long)seed,
                           (cudaStream_t)stream);
 }
 int b2v_ddpm_run(b2v_unet* u, const float* coef, int n, int first, int count, const float* noise, uint64_t seed,
                  void* stream) {
+  if (!u) return fail("ddpm_run: null handle");
   return u->u.ddpm_run(coef, n, first, count, noise, (unsigned long long)seed, (cudaStream_t)stream);
 }
 int b2v_ddim_timesteps(int n_train, int steps, int64_t* out, int cap) {
@@ -201,6 +212,7 @@ int b2v_eps_mse(const float* eps_pred, const float* noise, const float* mask, fl
   return check_launches("eps_mse");
 }
 int b2v_unet_profile(b2v_unet* u, int iters, char* buf, size_t cap, void* stream) {
+  if (!u) return fail("unet_profile: null handle");
   if (!u->u.last) return fail("unet_profile: run a forward first");
   u->u.last->temb = TembSource{u->u.last->proj, u->u.last->desc_rows, nullptr, 0};
   std::string js;
@@ -219,16 +231,23 @@ int b2v_vae_create(b2v_vae** out, const b2v_vae_desc* d) {
 }
 void b2v_vae_destroy(b2v_vae* v) { delete v; }
 int b2v_vae_load_weight(b2v_vae* v, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!v) return fail("vae_load_weight: null handle");
   return store_weight(v->v.wm, v->v.finalized, key, data, shape, ndim);
 }
-int b2v_vae_finalize(b2v_vae* v) { return v->v.finalize(); }
+int b2v_vae_finalize(b2v_vae* v) {
+  if (!v) return fail("vae_finalize: null handle");
+  return v->v.finalize();
+}
 int b2v_vae_encode(b2v_vae* v, const float* x, float* z, int B, int T, int H, int W, void* stream) {
+  if (!v) return fail("vae_encode: null handle");
   return v->v.encode(x, z, B, T, H, W, (cudaStream_t)stream);
 }
 int b2v_vae_decode(b2v_vae* v, const float* z, float* x, int B, int T, int h, int w, void* stream) {
+  if (!v) return fail("vae_decode: null handle");
   return v->v.decode(z, x, B, T, h, w, (cudaStream_t)stream);
 }
 int b2v_vae_profile(b2v_vae* v, int which, int iters, char* buf, size_t cap, void* stream) {
+  if (!v) return fail("vae_profile: null handle");
   if (which < 0 || which > 1 || !v->v.last[which]) return fail("vae_profile: run encode/decode first");
   std::string js;
   if (v->v.last[which]->prog.profile(iters, (cudaStream_t)stream, js)) return -1;
@@ -336,6 +355,7 @@ void b2v_conv_destroy(b2v_conv* c) {
 }
 int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, int64_t* stats, int groups,
                      int act_tanh, int N, int D, int H, int W, void* stream) {
+  if (!c) return fail("conv_forward: null handle");
   ConvPlan P;
   std::string err;
   const size_t need_ws = (out_fp32 && !in1 && !stats) ? conv_tap_ws_bytes(c->L, N, D, H, W) : 0;
