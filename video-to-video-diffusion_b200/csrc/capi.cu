@@ -102,7 +102,9 @@ int b2v_ddpm_step(b2v_unet* u, int64_t t, const float* coef, const float* noise,
   return u->u.ddpm_step((long long)t, coef, noise, (cudaStream_t)stream);
 }
 int b2v_sampler_end(b2v_unet* u, float* z_out, void* stream) {
-  if (!u) return fail("sampler_end: null handle"); return u->u.sampler_end(z_out, (cudaStream_t)stream); }
+  if (!u) return fail("sampler_end: null handle");
+  return u->u.sampler_end(z_out, (cudaStream_t)stream);
+}
 int b2v_ddpm_sample(b2v_unet* u, const float* z_init, const float* cond, float* z_out, int B, int T, int h, int w,
                     const float* coef, int n, const float* noise, uint64_t seed, void* stream) {
   if (!u) return fail("ddpm_sample: null handle");
