@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
     """samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs"""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -86,8 +86,9 @@ class ClockSampler(threading.Thread):
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i] == "Active" for s in self.samples)]
+        pw = sorted(float(s[6]) for s in self.samples if len(s) > 6 and s[6].replace(".", "", 1).isdigit())
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "power_w": pw[len(pw) // 2] if pw else None, "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
