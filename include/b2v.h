@@ -195,13 +195,6 @@ void b2v_conv_destroy(b2v_conv* c);
  * stats: NULL or int64 [N][groups][2], ACCUMULATED (zero it first) with the output's per-(sample, group) sums   */
 int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, int out_fp32, int64_t* stats,
                      int groups, int act_tanh, int N, int D, int H, int W, void* stream);
-/* ResBlock3D's conv1 (kind 0, 3x3x3) and its residual 1x1x1 convolution (kind 1) over the same input(s) in ONE launch
- * (models/unet3d.py:102,116-121): out = conv1(in), out_res = residual(in), both cl16; stats as in b2v_conv_forward
- * (of `out`).  *fused (HOST int, may be NULL) reports whether the pair shared a launch (1) or was run as two (0:
- * unequal shapes, split-K plans, B2V_NO_RESFUSE).                                                              */
-int b2v_conv_forward_with_residual(b2v_conv* conv1, b2v_conv* residual, const void* in0, const void* in1, void* out,
-                                   void* out_res, int64_t* stats, int groups, int N, int D, int H, int W, int* fused,
-                                   void* stream);
 int b2v_nc32_to_cl16(const float* in, void* out, int B, int C, int Cpad, long long S, void* stream);
 int b2v_cl16_to_nc32(const void* in, float* out, int B, int C, int Cpad, long long S, void* stream);
 /* out = silu(gn(y)) + temb (mode 0) or silu(gn(y) + res) (mode 1); stats_in as produced by b2v_conv_forward */

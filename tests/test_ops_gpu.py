@@ -101,50 +101,6 @@ def test_conv_vs_torch(cuda_dev, case, groups):
     assert torch.equal(out2, out) and torch.equal(stats2, stats), name
 
 
-RESFUSE_CASES = [
-    # name, cin0, cin1, cout, N, D, H, W          (kernel variant)
-    ("pair_256", 128, 0, 256, 2, 6, 12, 12),        # CTA-pair kernel, down1.0-like
-    ("pair_512_cat", 256, 256, 512, 1, 5, 6, 6),    # two sources (skip concat), up0.0-like; split-K plan at this size
-    ("pair_odd_tiles", 128, 0, 256, 3, 3, 6, 10),   # odd tile count: padded pair half
-    ("swapped_128_cat", 256, 128, 128, 2, 4, 16, 8),  # operand-swapped kernel, up3.0-like
-    ("plain_64", 128, 0, 64, 2, 3, 8, 8),           # single-CTA BN = 64 kernel
-    ("pair_big", 128, 64, 256, 4, 12, 24, 24),      # several waves: residual units fill the tail
-]
-
-
-@pytest.mark.parametrize("case", RESFUSE_CASES, ids=[c[0] for c in RESFUSE_CASES])
-def test_conv1_with_fused_residual_vs_torch(cuda_dev, case):
-    """the ResBlock's residual 1x1 conv rides in conv1's launch as extra work units (conv_params.h): both outputs and
-    conv1's statistics against torch, and bit for bit against the two separate launches"""
-    from v2v_b200 import ops
-    name, cin0, cin1, cout, N, D, H, W = case
-    g = torch.Generator().manual_seed(len(name) * 7 + cout)
-    cin = cin0 + cin1
-    x = torch.randn((N, cin, D, H, W), generator=g).to(cuda_dev)
-    w1, wr = _weight(0, cin, cout, g), _weight(1, cin, cout, g)
-    b1, br = torch.randn(cout, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1
-    c1, cr = ops.Conv(0, w1, b1, cin0, cin1, cout), ops.Conv(1, wr, br, cin0, cin1, cout)
-    x0 = ops.to_cl16(x[:, :cin0].contiguous())
-    x1 = ops.to_cl16(x[:, cin0:].contiguous()) if cin1 else None
-    out, out_res, stats, fused = ops.conv_with_residual(c1, cr, x0, x1, groups=8)
-    torch.cuda.synchronize()
-    ref1 = F.conv3d(_h(x), _h(w1).to(cuda_dev), b1.to(cuda_dev), padding=1)
-    refr = F.conv3d(_h(x), _h(wr).to(cuda_dev), br.to(cuda_dev))
-    ok, msg = _report(name + ".conv1", ops.from_cl16(out), ref1, 3e-3)
-    assert ok, msg
-    ok, msg = _report(name + ".residual", ops.from_cl16(out_res), refr, 3e-3)
-    assert ok, msg
-    rg = ref1.reshape(N, 8, -1)
-    ok, msg = _report(name + ".stats", ops.stats_to_float(stats).float(), torch.stack([rg.sum(-1), (rg * rg).sum(-1)], -1), 2e-3)
-    assert ok, msg
-    sep1, sep_stats = c1(x0, x1, groups=8)
-    sepr, _ = cr(x0, x1)
-    assert torch.equal(out, sep1) and torch.equal(out_res, sepr), (name, fused)
-    # (the statistics' per-CTA fp32 partials follow the tile -> CTA assignment, which the longer unit list may change)
-    assert torch.allclose(ops.stats_to_float(stats), ops.stats_to_float(sep_stats), rtol=1e-5, atol=1e-3)
-    print(f"{name}: fused={fused}")
-
-
 @pytest.mark.parametrize("cout,tanh", [(8, False), (1, True), (4, False)])
 def test_conv_head_fp32(cuda_dev, cout, tanh):
     from v2v_b200 import ops

@@ -113,27 +113,24 @@ def test_attention_fold_from_raw_depth_sums(splits):
     assert torch.allclose(out, ref, atol=1e-10)
 
 
-def _enumerate_units(m_tiles, n_tiles, nclass, splitk, ksteps, grid, pair, j2_chunks=0):
-    """host model of the unit walk in conv_igemm_kernel (conv_igemm.cuh: unit0 / unit_step / unit_k0 / unit_k1);
-    j2_chunks > 0: the fused residual 1x1 job follows the convolution's units (one tap, j2_chunks k-steps per tile)"""
+def _enumerate_units(m_tiles, n_tiles, nclass, splitk, ksteps, grid, pair):
+    """host model of the unit walk in conv_igemm_kernel (conv_igemm.cuh: unit0 / unit_step / unit_k0 / unit_k1)"""
     m_units = (m_tiles + 1) // 2 if pair else m_tiles
-    units1 = m_units * nclass * n_tiles * splitk
-    total_units = units1 + (m_units * n_tiles if j2_chunks else 0)
+    total_units = m_units * nclass * n_tiles * splitk
     workers = grid // 2 if pair else grid
     seen = []
     for worker in range(workers):
         for rank in range(2 if pair else 1):
             for unit in range(worker, total_units, workers):
-                j2 = unit >= units1
-                tile = unit - units1 if j2 else unit // splitk
+                tile = unit // splitk
                 m = 2 * (tile % m_units) + rank if pair else tile % m_units
                 rest = tile // m_units
-                cls, n = (0, rest) if j2 else (rest % nclass, rest // nclass)
-                k0 = 0 if j2 else (unit % splitk) * ksteps // splitk
-                k1 = j2_chunks if j2 else (unit % splitk + 1) * ksteps // splitk
+                cls, n = rest % nclass, rest // nclass
+                k0 = (unit % splitk) * ksteps // splitk
+                k1 = (unit % splitk + 1) * ksteps // splitk
                 if m >= m_tiles:
                     continue  # padding half of an odd pair: loads are zero-filled, the epilogue skips it
-                seen += [(m, cls, n, k) if not j2 else ("res", m, n, k) for k in range(k0, k1)]
+                seen += [(m, cls, n, k) for k in range(k0, k1)]
     return seen
 
 
@@ -144,15 +141,4 @@ def _enumerate_units(m_tiles, n_tiles, nclass, splitk, ksteps, grid, pair, j2_ch
 def test_persistent_unit_walk_covers_every_k_step_once(pair, m_tiles, n_tiles, nclass, splitk, ksteps, grid):
     seen = _enumerate_units(m_tiles, n_tiles, nclass, splitk, ksteps, grid, pair)
     want = set(itertools.product(range(m_tiles), range(nclass), range(n_tiles), range(ksteps)))
-    assert len(seen) == len(want) and set(seen) == want
-
-
-@pytest.mark.parametrize("pair", [False, True])
-@pytest.mark.parametrize("m_tiles,n_tiles,ksteps,chunks,grid", [(81, 1, 54, 2, 148), (56, 2, 432, 16, 148), (7, 2, 54, 2, 42),
-                                                                (1, 1, 27, 1, 2), (864, 1, 324, 12, 148)])
-def test_unit_walk_with_the_fused_residual_job(pair, m_tiles, n_tiles, ksteps, chunks, grid):
-    """conv1 + residual 1x1 in one launch: every conv (tile, k-step) and every residual (tile, chunk) exactly once"""
-    seen = _enumerate_units(m_tiles, n_tiles, 1, 1, ksteps, grid, pair, j2_chunks=chunks)
-    want = set(itertools.product(range(m_tiles), [0], range(n_tiles), range(ksteps)))
-    want |= set(("res", m, n, k) for m in range(m_tiles) for n in range(n_tiles) for k in range(chunks))
     assert len(seen) == len(want) and set(seen) == want

@@ -82,8 +82,6 @@ SIGNATURES = {
     "b2v_conv_create": (c_int, [POINTER(_P), c_int, _P, _P, c_int, c_int, c_int]),
     "b2v_conv_destroy": (None, [_P]),
     "b2v_conv_forward": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "b2v_conv_forward_with_residual": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
-                                               _P]),
     "b2v_nc32_to_cl16": (c_int, [_P, _P, c_int, c_int, c_int, c_longlong, _P]),
     "b2v_cl16_to_nc32": (c_int, [_P, _P, c_int, c_int, c_int, c_longlong, _P]),
     "b2v_gn_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, c_int, _P, c_int, _P]),

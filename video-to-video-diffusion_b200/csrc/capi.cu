@@ -387,38 +387,6 @@ int b2v_conv_forward(b2v_conv* c, const void* in0, const void* in1, void* out, i
   B2V_CUDA(cudaGetLastError());
   return 0;
 }
-int b2v_conv_forward_with_residual(b2v_conv* c1, b2v_conv* cr, const void* in0, const void* in1, void* out,
-                                   void* out_res, int64_t* stats, int groups, int N, int D, int H, int W, int* fused,
-                                   void* stream) {
-  if (!c1 || !cr || !in0 || !out || !out_res) return fail("conv_forward_with_residual: null argument");
-  ConvPlan P;
-  std::string err;
-  const size_t need_sk = conv_splitk_ws_bytes(c1->L, N, D, H, W);
-  if (need_sk > c1->sk_bytes) {
-    B2V_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    if (c1->sk) cudaFree(c1->sk);
-    c1->sk = nullptr;
-    c1->sk_bytes = 0;
-    B2V_CUDA(cudaMalloc(&c1->sk, need_sk));
-    c1->sk_bytes = need_sk;
-  }
-  if (conv_plan(P, c1->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out, OUT_CL16, (long long*)stats, groups,
-                ACT_NONE, err, nullptr, need_sk ? c1->sk : nullptr))
-    return fail(err);
-  const bool together = conv_plan_attach_residual(P, c1->L, cr->L, out_res) == 0;
-  if (fused) *fused = together ? 1 : 0;
-  conv_launch(P, (cudaStream_t)stream);
-  g_launches += (P.splitk > 1) ? 2 : 1;
-  if (!together) {
-    ConvPlan R;
-    if (conv_plan(R, cr->L, (const __half*)in0, (const __half*)in1, N, D, H, W, out_res, OUT_CL16, nullptr, 0, ACT_NONE,
-                  err, nullptr, nullptr))
-      return fail(err);
-    conv_launch(R, (cudaStream_t)stream);
-    g_launches += 1;
-  }
-  return check_launches("conv_forward_with_residual");
-}
 int b2v_nc32_to_cl16(const float* in, void* out, int B, int C, int Cpad, long long S, void* stream) {
   launch_nc32_to_cl16(in, (__half*)out, B, C, Cpad, S, (cudaStream_t)stream);
   g_launches += 1;

@@ -531,38 +531,6 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
   return 0;
 }
 
-int conv_plan_attach_residual(ConvPlan& P, const ConvLayer& L1, const ConvLayer& Lr, void* out2) {
-  static const bool off = getenv("B2V_NO_RESFUSE") != nullptr;  // A/B switch: the residual conv as its own launch
-  ConvParams& p = P.p;
-  if (off || P.tapgemm || P.splitk != 1 || L1.kind != CONV_K3 || Lr.kind != CONV_K1 || L1.nclass != 1 ||
-      p.out_mode != OUT_CL16 || p.act != ACT_NONE || L1.cin0_pad != Lr.cin0_pad || L1.cin1_pad != Lr.cin1_pad ||
-      L1.cout != Lr.cout || L1.bn != Lr.bn || L1.cout_pad != Lr.cout_pad)
-    return 1;
-  p.j2_on = 1;
-  p.tmB_j2 = Lr.tmB;
-  p.tmB2_j2 = Lr.tmB2;
-  p.out_j2 = out2;
-  p.bias_j2 = Lr.bias;
-  // the residual's work units extend the unit list: re-size the grid (small layers leave SMs idle that they can use)
-  const int sms = device_sm_count();
-  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
-  if (P.swapped) {
-    const long long total = (m_tiles / 2) * 2;  // conv pairs + residual pairs
-    P.grid = (int)(total < sms ? total : sms);
-  } else if (P.pair) {
-    const long long total = ((m_tiles + 1) / 2) * p.n_tiles * 2;
-    const long long clusters = total < sms / 2 ? total : sms / 2;
-    P.grid = (int)(2 * clusters);
-  } else {
-    const long long total = m_tiles * p.n_tiles * 2;
-    P.grid = (int)(total < sms ? total : sms);
-  }
-  const double pos = (double)p.batch * p.D * p.H * p.W;
-  P.flops += 2.0 * pos * (double)(Lr.cin0 + Lr.cin1) * (double)Lr.cout;
-  P.fused_residual = true;
-  return 0;
-}
-
 void conv_launch(const ConvPlan& P, cudaStream_t st) {
   if (P.tapgemm) {
     static const int dbg = getenv("B2V_TAP_DEBUG") ? atoi(getenv("B2V_TAP_DEBUG")) : 0;  // 1: GEMM only, 2: stencil only

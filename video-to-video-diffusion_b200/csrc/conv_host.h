@@ -63,7 +63,6 @@ struct ConvPlan {
     int C, G, B;
   } fin;
   double flops = 0;  // algorithmic 2*MAC of the reference convolution (no padding / packing waste)
-  bool fused_residual = false;
 };
 
 // w_host / b_host: fp32 host arrays in the torch layout of `kind`; b_host may be null (zero bias)
@@ -76,10 +75,6 @@ void conv_layer_free(ConvLayer& L);
 int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* in1, int N, int D, int H, int W,
               void* out, int out_mode, long long* stats, int groups, int act, std::string& err, float* tap_ws = nullptr,
               float* splitk_ws = nullptr);
-// Let the residual 1x1x1 convolution `Lr` of a ResBlock3D ride in the launch planned for its 3x3x3 conv1 `L1` (same
-// inputs, same output geometry; see conv_params.h): returns 0 if attached (out2 = the residual's cl16 output), 1 if the
-// pair is not fusable (the caller then launches the residual on its own), <0 never.
-int conv_plan_attach_residual(ConvPlan& P, const ConvLayer& L1, const ConvLayer& Lr, void* out2);
 // k-split factor the planner would use for this layer / input (1 = none) and the fp32 workspace it needs
 int conv_splitk_factor(const ConvLayer& L, int N, int D, int H, int W);
 size_t conv_splitk_ws_bytes(const ConvLayer& L, int N, int D, int H, int W);

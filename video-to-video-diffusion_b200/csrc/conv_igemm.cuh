@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;
   const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
   const int total_tiles = m_units * p.nclass * p.n_tiles;
-  const int units1 = total_tiles * p.splitk;                          // job 1: the convolution itself
-  const int total_units = units1 + (p.j2_on ? m_units * p.n_tiles : 0);  // job 2: the fused residual 1x1 conv
+  const int total_units = total_tiles * p.splitk;
   const int chunks = p.src_chunks0 + p.src_chunks1;
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -156,25 +155,22 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       uint32_t phase = 0;
       const int ksteps = p.ntaps * chunks;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const bool j2 = unit >= units1;  // residual 1x1 job: one centre tap, its own weights
-        const int tile = j2 ? unit - units1 : unit / p.splitk;
+        const int tile = unit / p.splitk;
         int m = PAIR ? 2 * (tile % m_units) + (int)rank : tile % m_units;
         int rest = tile / m_units;
-        const int cls = j2 ? 0 : rest % p.nclass;
-        const int n0 = (j2 ? rest : rest / p.nclass) * BN;
+        const int cls = rest % p.nclass;
+        const int n0 = (rest / p.nclass) * BN;
         const int w0 = (m % p.tiles_w) * p.bw;
         m /= p.tiles_w;
         const int h0 = (m % p.tiles_h) * p.bh;
         m /= p.tiles_h;
         const int d0 = (m % p.tiles_d) * p.bd;
         const int nb = m / p.tiles_d;  // == batch for the missing second tile of an odd count: TMA zero-fills it
-        const int k0 = j2 ? 0 : unit_k0(unit, ksteps, p.splitk), k1 = j2 ? chunks : unit_k1(unit, ksteps, p.splitk);
-        const CUtensorMap* tmB = j2 ? &p.tmB_j2 : &p.tmB;
-        const CUtensorMap* tmB2 = j2 ? &p.tmB2_j2 : &p.tmB2;
+        const int k0 = unit_k0(unit, ksteps, p.splitk), k1 = unit_k1(unit, ksteps, p.splitk);
         int t = k0 / chunks, c = k0 % chunks;
         for (int k = k0; k < k1; ++k) {
-          const int tg = j2 ? 0 : cls * p.ntaps + t;
-          const int32_t tp = j2 ? ((8 << 16) | (8 << 8) | 8) : p.taps[tg];
+          const int tg = cls * p.ntaps + t;
+          const int32_t tp = p.taps[tg];
           const int map = tp >> 24;
           const int cd = d0 + ((tp >> 16) & 0xff) - 8;
           const int chh = h0 + ((tp >> 8) & 0xff) - 8;
@@ -188,11 +184,11 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
             if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (a_bytes + (uint32_t)Cfg::B_BYTES));
             const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
             tma_load_5d_2sm(sa, &p.tmA[map + src], lbar, cc * 64, cw, chh, cd, nb);
-            tma_load_3d_2sm(sa + Cfg::A_BYTES, tmB2, lbar, c * 64, n0 + (int)rank * (BN / 2), tg);
+            tma_load_3d_2sm(sa + Cfg::A_BYTES, &p.tmB2, lbar, c * 64, n0 + (int)rank * (BN / 2), tg);
           } else {
             mbar_arrive_expect_tx(&full[stage], a_bytes + (uint32_t)Cfg::B_BYTES);
             tma_load_5d(sa, &p.tmA[map + src], &full[stage], cc * 64, cw, chh, cd, nb);
-            tma_load_3d(sa + Cfg::A_BYTES, tmB, &full[stage], c * 64, n0, tg);
+            tma_load_3d(sa + Cfg::A_BYTES, &p.tmB, &full[stage], c * 64, n0, tg);
           }
           if (++stage == NSTAGE) {
             stage = 0;
@@ -219,7 +215,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        const int nk = unit >= units1 ? chunks : unit_k1(unit, ksteps, p.splitk) - unit_k0(unit, ksteps, p.splitk);
+        const int nk = unit_k1(unit, ksteps, p.splitk) - unit_k0(unit, ksteps, p.splitk);
         for (int k = 0; k < nk; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -269,8 +265,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     int it = 0;
     const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
     for (int unit = unit0; unit < total_units; unit += unit_step, ++it) {
-      const bool j2 = unit >= units1;
-      const int tile = j2 ? unit - units1 : unit / p.splitk;
+      const int tile = unit / p.splitk;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int m = PAIR ? 2 * (tile % m_units) + (int)rank : tile % m_units;
@@ -282,11 +277,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         continue;
       }
       int rest = tile / m_units;
-      const int cls = j2 ? 0 : rest % p.nclass;
-      const int n0 = (j2 ? rest : rest / p.nclass) * BN;
-      const bool do_stats = p.stats && p.splitk == 1 && !j2;
-      const bool partial = p.splitk > 1 && !j2;
-      const float* bias = j2 ? p.bias_j2 : p.bias;
+      const int cls = rest % p.nclass;
+      const int n0 = (rest / p.nclass) * BN;
       const int w = (m % p.tiles_w) * p.bw + rw;
       m /= p.tiles_w;
       const int h = (m % p.tiles_h) * p.bh + rh;
@@ -295,7 +287,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       const int nb = m / p.tiles_d;
       const bool valid = (r < p.rows_valid) && (w < p.W) && (h < p.H) && (d < p.D);
       const long long roff = p.cls_off[cls] + nb * p.sN + d * p.sD + h * p.sH + w * p.sW;
-      if (do_stats) {
+      if (p.stats && p.splitk == 1) {
         const int key = nb * p.n_tiles + n0 / BN;
         if (key != cur_key) {
           if (cur_key >= 0) flush();
@@ -318,7 +310,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         tmem_ld_wait();
         const int cg = n0 + c0;
         if (cg >= p.cout_valid) break;
-        if (partial) {  // partial tile -> this k-split's slab of the workspace (same NDHWC indexing as the output)
+        if (p.splitk > 1) {  // partial tile -> this k-split's slab of the workspace (same NDHWC indexing as the output)
           if (valid) {
             float4* wsp = reinterpret_cast<float4*>(p.ws + (long long)(unit % p.splitk) * p.ws_slab + roff + cg);
 #pragma unroll
@@ -327,9 +319,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           continue;
         }
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] += __ldg(bias + cg + j);
+        for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + cg + j);
         if constexpr (CH == 32) {
-          if (do_stats) {
+          if (p.stats && p.splitk == 1) {
             const int gl = cg / p.cpg - cur_g0;
             if (p.cpg >= 32) chunk_stats<32>(v, valid, wstat, gl, lane);
             else if (p.cpg == 16) chunk_stats<16>(v, valid, wstat, gl, lane);
@@ -344,7 +336,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         }
         if (valid) {
           if (p.out_mode == OUT_CL16) {
-            __half* o = reinterpret_cast<__half*>(j2 ? p.out_j2 : p.out) + roff + cg;
+            __half* o = reinterpret_cast<__half*>(p.out) + roff + cg;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
               __half2 h0 = __floats2half2_rn(operand_round(v[j + 0]), operand_round(v[j + 1]));

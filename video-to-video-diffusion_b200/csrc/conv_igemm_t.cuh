@@ -50,8 +50,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.batch;  // even per sample (checked on the host)
   const int pairs = (m_tiles + 1) >> 1;
-  const int total1 = pairs * (MODE ? p.n_tiles : p.nclass);
-  const int total = total1 + ((MODE == 0 && p.j2_on) ? pairs : 0);  // + the fused residual 1x1 job (conv_params.h)
+  const int total = pairs * (MODE ? p.n_tiles : p.nclass);
   const int chunks = p.src_chunks0 + p.src_chunks1;
 
   if (threadIdx.x == 0) {
@@ -83,12 +82,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const bool j2 = tile >= total1;
-        const int cls = (MODE || j2) ? 0 : tile / pairs;
+        const int cls = MODE ? 0 : tile / pairs;
         const int n0 = MODE ? (tile / pairs) * 128 : 0;
         const int pm = tile % pairs;
-        const int ntaps = j2 ? 1 : p.ntaps;
-        const CUtensorMap* tmW = j2 ? &p.tmB_j2 : &p.tmB;
         int w0[2], h0[2], d0[2], nb[2];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -100,9 +96,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
           d0[hh] = (m % p.tiles_d) * p.bd;
           nb[hh] = m / p.tiles_d;
         }
-        for (int t = 0; t < ntaps; ++t) {
-          const int tg = j2 ? 0 : cls * p.ntaps + t;
-          const int32_t tp = j2 ? ((8 << 16) | (8 << 8) | 8) : p.taps[tg];
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int tg = cls * p.ntaps + t;
+          const int32_t tp = p.taps[tg];
           const int map = tp >> 24;
           const int od = ((tp >> 16) & 0xff) - 8, oh = ((tp >> 8) & 0xff) - 8, ow = (tp & 0xff) - 8;
           for (int c = 0; c < chunks; ++c) {
@@ -111,7 +107,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], 2u * a_bytes + (uint32_t)Cfg::W_BYTES);
             uint8_t* sa = smem + stage * Cfg::STAGE;
-            tma_load_3d(sa, tmW, &full[stage], c * 64, n0, tg);
+            tma_load_3d(sa, &p.tmB, &full[stage], c * 64, n0, tg);
             tma_load_5d(sa + Cfg::W_BYTES, &p.tmA[map + src], &full[stage], cc * 64, w0[0] + ow, h0[0] + oh,
                         d0[0] + od, nb[0]);
             tma_load_5d(sa + Cfg::W_BYTES + 16384, &p.tmA[map + src], &full[stage], cc * 64, w0[1] + ow, h0[1] + oh,
@@ -137,8 +133,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-        const int nk = tile >= total1 ? chunks : ksteps;
-        for (int k = 0; k < nk; ++k) {
+        for (int k = 0; k < ksteps; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE);
@@ -163,7 +158,6 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     const int et = threadIdx.x - 64;
     const int ng = 128 / p.cpg;
     const float bias_c = MODE ? 0.f : __ldg(p.bias + ch);
-    const float bias_c2 = (MODE == 0 && p.j2_on) ? __ldg(p.bias_j2 + ch) : 0.f;
     __half* xp = xpose + (warp - 2) * 1024;  // 32 positions x 32 channels (MODE 0)
     __half* outp = reinterpret_cast<__half*>(p.out);
     int cur_nb = -1;
@@ -180,12 +174,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const bool j2 = tile >= total1;
-      const int cls = (MODE || j2) ? 0 : tile / pairs;
+      const int cls = MODE ? 0 : tile / pairs;
       const int pm = tile % pairs;
-      const bool do_stats = p.stats && !j2;
-      const float bias_u = j2 ? bias_c2 : bias_c;
-      __half* outu = j2 ? reinterpret_cast<__half*>(p.out_j2) : outp;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
@@ -228,7 +218,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         const bool valid = (r < p.rows_valid) && (w < p.W) && (h < p.H) && (d < p.D);
         const long long roff = p.cls_off[cls] + nb * p.sN + d * p.sD + h * p.sH + w * p.sW;
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-        if (do_stats && nb != cur_nb) {  // nb is uniform over the tile (pairs never straddle samples)
+        if (p.stats && nb != cur_nb) {  // nb is uniform over the tile (pairs never straddle samples)
           if (cur_nb >= 0) flush();
           cur_nb = nb;
         }
@@ -236,8 +226,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         tmem_ld_32x32(taddr + ci * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias_u;
-        if (do_stats) {
+        for (int j = 0; j < 32; ++j) v[j] += bias_c;
+        if (p.stats) {
           float s = 0.f, ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -266,7 +256,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
           const int cs = (lane & 3) * 8;
           const uint4 val = *reinterpret_cast<const uint4*>(xp + pl * 32 + cs);
           const long long off = __shfl_sync(0xffffffffu, roff, pl);
-          if ((vmask >> pl) & 1u) *reinterpret_cast<uint4*>(outu + off + q * 32 + cs) = val;
+          if ((vmask >> pl) & 1u) *reinterpret_cast<uint4*>(outp + off + q * 32 + cs) = val;
         }
         __syncwarp();
       }

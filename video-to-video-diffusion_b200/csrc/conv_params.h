@@ -27,13 +27,6 @@ struct ConvParams {
   int splitk;             // k-splits per output tile (1 = off)
   float* ws;              // split-K fp32 workspace: splitk slabs, each NDHWC like the output
   long long ws_slab;      // elements per slab
-  // Second job riding in the same launch: the 1x1x1 residual convolution of a ResBlock3D (models/unet3d.py:102,121),
-  // which reads exactly the A tiles conv1's centre tap reads.  Same tiling, same output geometry; its work units follow
-  // conv1's in the unit list, so they fill the last, partially occupied wave.  j2_on == 0: absent.
-  int j2_on;
-  CUtensorMap tmB_j2, tmB2_j2;  // residual weights [1][Cout_pad][Cin_total] (full / half-height box)
-  void* out_j2;
-  const float* bias_j2;
 };
 
 }  // namespace b2v

@@ -241,8 +241,7 @@ stat_t* Builder::new_stats(int G) {
 }
 
 Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, stat_t* stats,
-                  int groups, float* out_fp32, int act, const float* bias_override, const ConvLayer* residual,
-                  Act* res_out) {
+                  int groups, float* out_fp32, int act, const float* bias_override) {
   Act out;
   int oD = in0.D, oH = in0.H, oW = in0.W;
   if (L.kind == CONV_DOWN) {
@@ -294,19 +293,8 @@ Act Builder::conv(const std::string& name, const ConvLayer& L, const Act& in0, c
     P.p.bias = bias_override;
     P.fin.bias = bias_override;
   }
-  bool fused = false;
-  if (residual && res_out && !out_fp32) {
-    Act rr = alloc(L.cout, oD, oH, oW);
-    if (!ok) return out;
-    if (conv_plan_attach_residual(P, L, *residual, rr.p) == 0) {
-      *res_out = rr;
-      fused = true;
-    } else {
-      free(rr);
-    }
-  }
   Op op;
-  op.name = fused ? name + "+residual_conv" : name;
+  op.name = name;
   op.flops = P.flops;
   op.bytes = 0;
   op.launches = (P.tapgemm || P.splitk > 1) ? 2 : 1;

@@ -121,11 +121,8 @@ struct Builder {
   void free(Act& a);
   stat_t* new_stats(int G);
   // out_fp32 != nullptr: NCDHW fp32 head; otherwise returns a fresh cl16 activation
-  // residual != nullptr: try to let that 1x1 conv ride in the same launch (conv_plan_attach_residual); *res_out
-  // receives its output activation, or stays empty (p == nullptr) when the pair is not fusable
   Act conv(const std::string& name, const ConvLayer& L, const Act& in0, const Act* in1, stat_t* stats, int groups,
-           float* out_fp32 = nullptr, int act = ACT_NONE, const float* bias_override = nullptr,
-           const ConvLayer* residual = nullptr, Act* res_out = nullptr);
+           float* out_fp32 = nullptr, int act = ACT_NONE, const float* bias_override = nullptr);
   // temb_off >= 0: add row offset temb_off of the time-embedding table (*temb_src) after the SiLU (mode 0)
   void gn_apply(const std::string& name, Act& y, const stat_t* stats_in, const GNW& g, int temb_off, const Act* res,
                 int mode, stat_t* stats_out, int G_out);

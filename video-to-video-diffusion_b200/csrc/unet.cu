@@ -199,11 +199,9 @@ struct UBuild {
   Act res(const std::string& name, const ResW& r, const Act& x, const Act* skip, stat_t** out_stats, int G_out,
           float** tsum_out = nullptr, int* ts_out = nullptr) {
     stat_t* s1 = b.new_stats(r.n1.G);
+    Act y1 = b.conv(name + ".conv1", r.conv1, x, skip, s1, r.n1.G);
     Act rr;
-    // the residual 1x1 conv reads the very tiles conv1's centre tap reads: it rides in conv1's launch when it can
-    Act y1 = b.conv(name + ".conv1", r.conv1, x, skip, s1, r.n1.G, nullptr, ACT_NONE, nullptr,
-                    r.has_res ? &r.res : nullptr, r.has_res ? &rr : nullptr);
-    if (r.has_res && !rr.p) rr = b.conv(name + ".residual_conv", r.res, x, skip, nullptr, 0);
+    if (r.has_res) rr = b.conv(name + ".residual_conv", r.res, x, skip, nullptr, 0);
     b.gn_apply(name + ".gn1_silu_temb", y1, s1, r.n1, r.temb_off, nullptr, 0, nullptr, 0);
     stat_t* s2 = b.new_stats(r.n2.G);
     Act y2 = b.conv(name + ".conv2", r.conv2, y1, nullptr, s2, r.n2.G);

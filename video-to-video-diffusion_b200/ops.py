@@ -76,21 +76,6 @@ class Conv:
             pass
 
 
-def conv_with_residual(conv1, residual, x0, x1=None, groups=0):
-    """ResBlock conv1 (3x3x3) + its residual 1x1 conv over the same input(s), one launch when the plans allow it.
-    Returns (out, out_res, stats, fused)."""
-    B, D, H, W, _ = x0.shape
-    out = torch.empty((B, D, H, W, conv1.cout), dtype=torch.float16, device=x0.device)
-    out_res = torch.empty_like(out)
-    stats = torch.zeros((B, groups, 2), dtype=torch.int64, device=x0.device) if groups else None
-    fused = ctypes.c_int(-1)
-    _lib.check(_lib.lib().b2v_conv_forward_with_residual(
-        conv1._h, residual._h, _lib.dptr(x0, torch.float16), _lib.dptr(x1, torch.float16), _lib.dptr(out, torch.float16),
-        _lib.dptr(out_res, torch.float16), _lib.dptr(stats, torch.int64), groups, B, D, H, W, ctypes.byref(fused),
-        _lib.stream()), "conv_forward_with_residual")
-    return out, out_res, stats, bool(fused.value)
-
-
 def gn_apply(y, stats, gamma, beta, groups, temb=None, res=None, mode=0, groups_out=0):
     """y: cl16 (B,D,H,W,C).  mode 0: silu(gn(y)) + temb ; mode 1: silu(gn(y) + res).  Returns (out, stats_out)."""
     B, D, H, W, C = y.shape
