@@ -464,6 +464,29 @@ def test_config5_stitched_volume_vs_oracle(cuda_dev, bench_model):
     assert got.shape == ref.shape and err < 0.1 and p > 35.0, (err, p)  # free-running DDIM-2, like the config-3 test
 
 
+def test_unet_192_channels_group_widths_that_are_not_powers_of_two(cuda_dev):
+    """model_channels = 192 (a multiple of 64 the reference accepts): 24 and 6 channels per GroupNorm group, so the conv
+    epilogue's power-of-two statistics fold does not apply and the planner inserts a statistics pass; Cout = 192 / 384
+    run on the BN = 64 / 128 single-CTA conv kernels (such configs used to fail at program-build time)"""
+    from v2v_b200.models import UNet3D
+    cfg = dict(latent_dim=4, model_channels=192, num_res_blocks=1, attention_levels=[1], channel_mult=(1, 2), num_heads=2,
+               time_embed_dim=128)
+    torch.manual_seed(3)
+    m = UNet3D(**cfg).eval().to(cuda_dev)
+    sd = _sd(m, cuda_dev)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn((2, 4, 5, 8, 12), generator=g).to(cuda_dev)
+    c = torch.randn((2, 4, 5, 8, 12), generator=g).to(cuda_dev)
+    t = torch.tensor([999, 17], device=cuda_dev)
+    with torch.no_grad():
+        ref = R.unet_forward(sd, cfg, x, t, c)
+    got = m(x, t, c)
+    err = rel_l2(got, ref)
+    print(f"U-Net with model_channels 192: rel-L2 = {err:.3e}")
+    assert err < EPS_TOL, err
+    assert torch.equal(m(x, t, c), got)
+
+
 def test_ragged_shapes_empty_batch_and_nan_input(cuda_dev):
     """edge cases: odd depth / non-square latent (partial TMA boxes everywhere), batch 3, empty batch, NaNs in v_in"""
     from v2v_b200.models import VideoToVideoDiffusion
