@@ -534,35 +534,35 @@ int conv_plan(ConvPlan& P, const ConvLayer& L, const __half* in0, const __half* 
 void conv_launch(const ConvPlan& P, cudaStream_t st) {
   if (P.tapgemm) {
     static const int dbg = getenv("B2V_TAP_DEBUG") ? atoi(getenv("B2V_TAP_DEBUG")) : 0;  // 1: GEMM only, 2: stencil only
-    if (dbg != 2) launch_k(conv_igemm_t_kernel<1>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
+    if (dbg != 2) launch_k(conv_igemm_t_kernel<1>, dim3(P.grid), dim3(ConvCfgT::threads(1)), ConvCfgT::SMEM, st, P.p);
     if (dbg != 1) launch_head_stencil(P.st.P, P.st.bias, P.st.out, P.st.N, P.st.cout, P.st.D, P.st.H, P.st.W, P.st.row_stride,
                         P.st.slice_stride, P.st.act, st);
     return;
   }
   if (P.swapped) {
-    launch_k(conv_igemm_t_kernel<0>, dim3(P.grid), dim3(192), ConvCfgT::SMEM, st, P.p);
+    launch_k(conv_igemm_t_kernel<0>, dim3(P.grid), dim3(ConvCfgT::threads(0)), ConvCfgT::SMEM, st, P.p);
     return;
   }
   if (P.splitk > 1) {
-    if (P.pair) launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(192), ConvCfg<256, true>::SMEM, st, P.p);
+    if (P.pair) launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(ConvCfg<256, true>::THREADS), ConvCfg<256, true>::SMEM, st, P.p);
     else switch (P.bn) {
-      case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(192), ConvCfg<64>::SMEM, st, P.p); break;
-      case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
-      default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
+      case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(ConvCfg<64>::THREADS), ConvCfg<64>::SMEM, st, P.p); break;
+      case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(ConvCfg<128>::THREADS), ConvCfg<128>::SMEM, st, P.p); break;
+      default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(ConvCfg<256>::THREADS), ConvCfg<256>::SMEM, st, P.p); break;
     }
     launch_splitk_finalize(P.fin.ws, P.fin.slab, P.splitk, P.fin.bias, P.fin.out, P.fin.stats, P.fin.B, P.fin.S,
                            P.fin.C, P.fin.G, st);
     return;
   }
   if (P.pair) {
-    launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(192), ConvCfg<256, true>::SMEM, st, P.p);
+    launch_k_pair(conv_igemm_kernel<256, true>, dim3(P.grid), dim3(ConvCfg<256, true>::THREADS), ConvCfg<256, true>::SMEM, st, P.p);
     return;
   }
   switch (P.bn) {
-    case 16: launch_k(conv_igemm_kernel<16>, dim3(P.grid), dim3(192), ConvCfg<16>::SMEM, st, P.p); break;
-    case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(192), ConvCfg<64>::SMEM, st, P.p); break;
-    case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(192), ConvCfg<128>::SMEM, st, P.p); break;
-    default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(192), ConvCfg<256>::SMEM, st, P.p); break;
+    case 16: launch_k(conv_igemm_kernel<16>, dim3(P.grid), dim3(ConvCfg<16>::THREADS), ConvCfg<16>::SMEM, st, P.p); break;
+    case 64: launch_k(conv_igemm_kernel<64>, dim3(P.grid), dim3(ConvCfg<64>::THREADS), ConvCfg<64>::SMEM, st, P.p); break;
+    case 128: launch_k(conv_igemm_kernel<128>, dim3(P.grid), dim3(ConvCfg<128>::THREADS), ConvCfg<128>::SMEM, st, P.p); break;
+    default: launch_k(conv_igemm_kernel<256>, dim3(P.grid), dim3(ConvCfg<256>::THREADS), ConvCfg<256>::SMEM, st, P.p); break;
   }
 }
 

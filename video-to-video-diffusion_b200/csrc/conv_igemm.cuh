@@ -32,7 +32,11 @@ struct ConvCfg {
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 4096 /*group stats, per warp*/;
+  // epilogue warps: two per TMEM lane quarter for the wide tiles (each takes half of the tile's columns), so the one
+  // epilogue nothing overlaps -- the last tile's -- and the short-K layers' epilogues take half as long
+  static constexpr int EW = (BN >= 64) ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EW;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 * EW /*group stats, per warp*/;
 };
 
 // Sum N per-lane values across the 32 lanes of a warp with N-1 + log2(32/N) shuffles (instead of 5 per value):
@@ -92,9 +96,10 @@ __device__ __forceinline__ int unit_k1(int unit, int ksteps, int S) {
 }
 
 template <int BN, bool PAIR = false>
-__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(ConvCfg<BN, PAIR>::THREADS, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN, PAIR>;
   constexpr int NSTAGE = Cfg::NSTAGE;
+  constexpr int EW = Cfg::EW;
   constexpr int CH = (BN >= 32) ? 32 : 16;  // epilogue column chunk
 
   extern __shared__ uint8_t smem_raw[];
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // [4 epilogue warps][<=128 groups][2]
+  float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);  // [EW epilogue warps][<=128 groups][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], PAIR ? 8 : 4);  // PAIR: the epilogue warps of both CTAs release the leader's accumulator
+      mbar_init(&tempty[i], PAIR ? 2 * EW : EW);  // PAIR: the epilogue warps of both CTAs release the leader's accumulator
     }
     fence_mbar_init();
   }
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, Cfg::TM_COLS);
     else tmem_alloc(tmem_slot, Cfg::TM_COLS);
   }
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 256 * EW; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   else __syncthreads();
@@ -241,26 +246,33 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..2+EW-1)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int EG = EW / 4;                    // warps per lane quarter
+    const int eg = (warp - 2) >> 2;               // which share of the tile's columns this warp handles
+    constexpr int COLS = (BN / EG < CH) ? CH : BN / EG;
     const int r = q * 32 + lane;
     const int rw = r % p.bw;
     const int rh = (r / p.bw) % p.bh;
     const int rd = r / (p.bw * p.bh);
-    const int et = threadIdx.x - 64;           // 0..127 within the epilogue warps
+    const int et = threadIdx.x - 64;           // 0..32*EW-1 within the epilogue warps
     const int ng = (BN + p.cpg - 1) / p.cpg;   // groups touched by one n-tile
     int cur_key = -1, cur_nb = 0, cur_g0 = 0;
     float* wstat = sstat + (warp - 2) * 256;  // this warp's table
     // flush the CTA-local group statistics: one global fixed-point atomic per (group, moment)
     auto flush = [&]() {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       if (et < 2 * ng) {
-        const float val = ((sstat[et] + sstat[256 + et]) + sstat[512 + et]) + sstat[768 + et];
-        sstat[et] = sstat[256 + et] = sstat[512 + et] = sstat[768 + et] = 0.f;
+        float val = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < EW; ++wi) {  // the warps' tables in index order: fixed summation order
+          val += sstat[wi * 256 + et];
+          sstat[wi * 256 + et] = 0.f;
+        }
         const int g = cur_g0 + (et >> 1);
         if (g < p.groups) stat_add(p.stats + ((size_t)cur_nb * p.groups + g) * 2 + (et & 1), val);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
     };
     int it = 0;
     const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int c0 = eg * COLS; c0 < (eg + 1) * COLS && c0 < BN; c0 += CH) {
         float v[CH];
         if constexpr (CH == 32)
           tmem_ld_32x32(taddr + c0, v);
@@ -318,8 +330,14 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           }
           continue;
         }
+        {  // the chunk's biases as 16-byte loads (cg is a multiple of 16: aligned)
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + cg);
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + cg + j);
+          for (int j = 0; j < CH; j += 4) {
+            const float4 bb = __ldg(b4 + j / 4);
+            v[j] += bb.x, v[j + 1] += bb.y, v[j + 2] += bb.z, v[j + 3] += bb.w;
+          }
+        }
         if constexpr (CH == 32) {
           if (p.stats && p.splitk == 1) {
             const int gl = cg / p.cpg - cur_g0;

@@ -22,8 +22,12 @@ struct ConvCfgT {
   static constexpr int STAGE = W_BYTES + P_BYTES;
   static constexpr int NSTAGE = 4;
   static constexpr int TM_COLS = 512;
-  static constexpr int XPOSE = 4 * 32 * 33 * 4;  // per-epilogue-warp transpose tile (32x32 fp16, or 32x33 fp32 in MODE 1)
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + 1024 + XPOSE;
+  static constexpr int XPOSE = 4 * 32 * 33 * 4;  // transpose tiles: 8 warps x 32x32 fp16 (MODE 0) or 4 warps x 32x33 fp32 (MODE 1)
+  static constexpr int STATS = 2048;             // [2 epilogue warp groups][<=128 groups][2] floats
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + STATS + XPOSE;
+  // epilogue warps: MODE 0 runs two per TMEM lane quarter (each takes four of the tile's eight 32-position chunks)
+  static constexpr int ew(int mode) { return mode == 0 ? 8 : 4; }
+  static constexpr int threads(int mode) { return 64 + 32 * ew(mode); }
 };
 
 // MODE 0: convolution (above).  MODE 1 ("tap GEMM", narrow heads Cout <= 16): the 128 "channel" rows are
@@ -33,9 +37,10 @@ struct ConvCfgT {
 // in-plane shifted rows.  The input is read 3 times (L2 hits) instead of 27 (the N=16 implicit GEMM was L2-bound at
 // ~7 TB/s) and P is 9*Cout rows (a 27*Cout-row P with the input read once spilled the L2: 382 MB for the U-Net head).
 template <int MODE>
-__global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(ConvCfgT::threads(MODE), 1) conv_igemm_t_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfgT;
   constexpr int NSTAGE = Cfg::NSTAGE;
+  constexpr int EW = Cfg::ew(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * Cfg::STAGE);
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* sstat = reinterpret_cast<float*>(smem + NSTAGE * Cfg::STAGE + 256);
-  __half* xpose = reinterpret_cast<__half*>(smem + NSTAGE * Cfg::STAGE + 256 + 1024);
+  __half* xpose = reinterpret_cast<__half*>(smem + NSTAGE * Cfg::STAGE + 256 + Cfg::STATS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,12 +67,12 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], EW);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TM_COLS);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,19 +161,22 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
     const int q = warp & 3;
     const int ch = q * 32 + lane;
     const int et = threadIdx.x - 64;
+    const int eg = (warp - 2) >> 2;      // 0 / 1: which four chunks of the tile this warp handles (MODE 0)
+    float* gstat = sstat + eg * 256;     // this warp group's table (a group's entry has ONE writer lane: fixed order)
+    constexpr int CHUNKS = 32 / EW;      // chunks per warp: 4 with eight epilogue warps, 8 with four
     const int ng = 128 / p.cpg;
     const float bias_c = MODE ? 0.f : __ldg(p.bias + ch);
     __half* xp = xpose + (warp - 2) * 1024;  // 32 positions x 32 channels (MODE 0)
     __half* outp = reinterpret_cast<__half*>(p.out);
     int cur_nb = -1;
     auto flush = [&]() {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       if (et < 2 * ng) {
-        const float val = sstat[et];
-        sstat[et] = 0.f;
+        const float val = sstat[et] + sstat[256 + et];  // the two warp groups' tables, in index order
+        sstat[et] = sstat[256 + et] = 0.f;
         stat_add(p.stats + ((size_t)cur_nb * p.groups + (et >> 1)) * 2 + (et & 1), val);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
         }
       } else {
 #pragma unroll 1
-      for (int ci = 0; ci < 8; ++ci) {
+      for (int ci = eg * CHUNKS; ci < (eg + 1) * CHUNKS; ++ci) {
         // this lane's "own" position of the chunk: row r of box (ci >> 2)
         int m = 2 * pm + (ci >> 2);
         const int r = (ci & 3) * 32 + lane;
@@ -242,8 +250,8 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_t_kernel(const __grid_const
           // a group is owned by ONE lane of ONE warp (cpg <= 32 adjacent channels): plain read-modify-write in
           // program order, so the CTA's partial sums are built in the same order in every run
           if ((lane & (p.cpg - 1)) == 0) {
-            sstat[(ch / p.cpg) * 2] += s;
-            sstat[(ch / p.cpg) * 2 + 1] += ss;
+            gstat[(ch / p.cpg) * 2] += s;
+            gstat[(ch / p.cpg) * 2 + 1] += ss;
           }
         }
         // 32 channels x 32 positions -> [position][channel] through shared memory, then 16-byte row stores
